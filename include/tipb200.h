@@ -1,0 +1,171 @@
+/* libtipb200 -- C ABI of the B200-native TIP tri-graph encoder/decoder hot path.
+ *
+ * This is the drop-in boundary.  The reference (NYXFLOWER/TIP) is pure Python:
+ * its operators are torch.nn.Module.forward methods in src/layers.py that bottom out in
+ * torch_geometric / torch_scatter / ATen kernels.  Each entry point below replaces the device work
+ * of one of those call sites; the reference line it stands in for is cited on every declaration
+ * (paths relative to the reference root).  The Python mirror of the reference's module API lives in
+ * tip_b200/layers.py and binds these symbols through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns TIPB_OK (0) or a negative TIPB_ERR_* code; tipb_last_error() gives the
+ *     thread-local message.  Nothing throws, exits or allocates: all outputs and all scratch memory
+ *     are caller-owned device buffers (sizes from the *_bytes queries, which make no CUDA calls).
+ *   - pointers are device pointers on the current device, 16-byte aligned, row-major, dense.
+ *     Indices arrive as int64 exactly as the reference's LongTensors; floats are fp32.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) with no host synchronisation,
+ *     so every call is CUDA-graph capturable.  No floating-point atomics: results are
+ *     run-to-run deterministic.
+ *   - there is no CPU fallback.
+ */
+#ifndef TIPB200_H
+#define TIPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIPB_VERSION 100
+
+#define TIPB_OK 0
+#define TIPB_ERR_INVALID_ARGUMENT (-1)
+#define TIPB_ERR_CUDA (-2)
+#define TIPB_ERR_UNSUPPORTED (-3)
+
+int tipb_version(void);
+const char* tipb_last_error(void);
+
+/* ---------------------------------------------------------------- primitives (exported for tests) */
+size_t tipb_scan_workspace_bytes(int64_t n);
+int tipb_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1: out[n] = total */, int64_t n, void* ws,
+                            size_t ws_bytes, void* stream);
+size_t tipb_sort_workspace_bytes(int64_t n);
+/* stable LSD radix sort on the low key_bits bits; result in (keys_out, vals_out), inputs clobbered */
+int tipb_sort_pairs_u32(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int64_t n,
+                        int key_bits, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- typed CSR ("plan")
+ * Replaces: the relation range_list layout of src/utils.py:26-32 + the per-call
+ * x.index_select / torch_scatter index handling inside MessagePassing.propagate
+ * (src/layers.py:78-79,159-160,230).  Built once per graph and cached by the caller.
+ * Field order of the plan buffer (int32 arrays unless noted): */
+enum {
+    TIPB_CSR_COUNTS = 0,   /* [16]  see TIPB_CSR_COUNT_* */
+    TIPB_CSR_EID,          /* [entries]   input position of each sorted entry (>= n_edges: reversed copy) */
+    TIPB_CSR_OTHER,        /* [entries]   opposite endpoint */
+    TIPB_CSR_SEG_PTR,      /* [seg_cap+1] entry offsets of the non-empty (node, relation) segments */
+    TIPB_CSR_SEG_NODE,     /* [seg_cap] */
+    TIPB_CSR_SEG_REL,      /* [seg_cap] */
+    TIPB_CSR_NODE_PTR,     /* [n_nodes+1] segment offsets per node */
+    TIPB_CSR_DEG,          /* [n_nodes]   entries per node */
+    TIPB_CSR_INV_DEG,      /* [n_nodes]   float: 1 / max(deg, 1)  (torch_scatter mean's clamp) */
+    TIPB_CSR_REL_SEG_PTR,  /* [n_rel+1] */
+    TIPB_CSR_REL_SEG,      /* [seg_cap]   segment ids listed relation-major */
+    TIPB_CSR_NFIELDS
+};
+enum {
+    TIPB_CSR_COUNT_SEGMENTS = 0, /* S: number of non-empty segments */
+    TIPB_CSR_COUNT_VALID = 1,    /* entries kept (self loops / out-of-range entries are dropped) */
+    TIPB_CSR_COUNT_STATUS = 2    /* bit0: an index was out of range */
+};
+size_t tipb_typed_csr_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel);
+size_t tipb_typed_csr_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel);
+int tipb_typed_csr_layout(int64_t n_entries, int64_t n_nodes, int64_t n_rel,
+                          int64_t* offsets_bytes /* [TIPB_CSR_NFIELDS] */, int64_t* seg_capacity);
+/* edge_type may be NULL when range_list ([n_rel,2], cumulative) is given, and both may be NULL when
+ * n_rel == 1.  by_src=0 groups by edge_index[1] (message target), 1 by edge_index[0].
+ * doubled=1 lists each edge in both directions (n_entries = 2*n_edges). */
+int tipb_typed_csr_build(const int64_t* edge_index /* [2,n_edges] */, const int64_t* edge_type,
+                         const int64_t* range_list, int64_t n_edges, int64_t n_nodes, int64_t n_other,
+                         int64_t n_rel, int by_src, int doubled, int drop_self_loops, void* plan, size_t plan_bytes,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- R-GCN with basis decomposition
+ * Replaces MyRGCNConv.forward / MyRGCNConv2.forward (src/layers.py:76-94, 157-188) and their
+ * autograd backward:   out_i = 1/max(deg_i,1) * sum_{e=(j->i), r=type(e)} x_j W_r + x_i root (+ bias),
+ *                      W_r = sum_b att[r,b] basis[b].
+ * Evaluated as  H[s] = sum_{e in segment s} x_j   (segmented gather-reduce over the typed CSR),
+ *               G[i,b,:] = sum_{s in node i} att[rel_s,b] H[s]  and  out_i = inv_deg_i G[i] . basis + x_i root.
+ * `g_saved` ([n_nodes, n_bases, f_in], written by fwd) is what bwd needs for d_basis. */
+size_t tipb_rgcn_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel, int f_in, int f_out, int n_bases);
+int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, int64_t n_rel, const float* x,
+                  const float* basis, const float* att, const float* root, const float* bias /* or NULL */,
+                  int f_in, int f_out, int n_bases, int relu_out, float* out, float* g_saved, void* ws,
+                  size_t ws_bytes, void* stream);
+int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, int64_t n_rel,
+                  const float* inv_deg_dst /* TIPB_CSR_INV_DEG of the by-dst plan */, const float* x,
+                  const float* basis, const float* att, const float* root, const float* g_saved,
+                  const float* grad_out, const float* out_for_relu /* fwd output when relu_out, else NULL */,
+                  int f_in, int f_out, int n_bases, float* d_x, float* d_basis, float* d_att, float* d_root,
+                  float* d_bias /* or NULL */, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- P-P GCN (symmetric-normalised SpMM)
+ * Replaces torch_geometric GCNConv(cached=True).forward as called from PPEncoder
+ * (src/layers.py:386-387, 391-395): out = D^-1/2 (A + I) D^-1/2 x + bias, D = in-degree + 1,
+ * existing self loops dropped (add_remaining_self_loops).  The plan is a typed CSR with n_rel = 1
+ * built with drop_self_loops = 1; the by-src plan of the same graph drives the backward pass. */
+int tipb_gcn_norm(const void* plan, int64_t n_entries, int64_t n_nodes, float* dis /* [n_nodes] deg^-1/2 */,
+                  void* stream);
+/* out[i] = dis_out[i] * ( sum_{j in N(i)} dis_in[j] x[j] + dis_in[i] x[i] ) + bias ; optional ReLU */
+int tipb_gcn_spmm(const void* plan, int64_t n_entries, int64_t n_nodes, const float* dis_out, const float* dis_in,
+                  const float* x, const float* bias /* or NULL */, int f, int relu, float* out, void* stream);
+
+/* ---------------------------------------------------------------- P->D hierarchy conv
+ * Replaces MyHierarchyConv.forward (src/layers.py:229-242): mean over incoming edges on the rows
+ * [n_source, n_source+n_target), times weight[f_in, f_out].  `mean` ([n_target, f_in]) is saved for bwd. */
+size_t tipb_hier_workspace_bytes(int64_t n_source, int64_t n_target, int f_in, int f_out);
+int tipb_hier_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_source, int64_t n_target, const float* x,
+                  const float* weight, int f_in, int f_out, float* mean, float* out, void* stream);
+int tipb_hier_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_source, int64_t n_target,
+                  const float* inv_deg_dst, const float* mean, const float* weight, const float* grad_out,
+                  int f_in, int f_out, float* d_x /* [n_source+n_target,f_in] */, float* d_weight, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- DistMult decoder
+ * Replaces MultiInnerProductDecoder.forward (src/layers.py:590-592):
+ *   value_e = sum_k z[i_e,k] z[j_e,k] weight[r_e,k];  score = sigmoid(value) (or value). */
+int tipb_decoder_fwd(const float* z, const float* weight, const int64_t* edge_index, const int64_t* edge_type,
+                     int64_t n_edges, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid, float* out,
+                     void* stream);
+/* d_score -> d_z, d_weight for an arbitrary edge list, through a doubled typed CSR of that list */
+size_t tipb_decoder_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t n_rel, int dim);
+int tipb_decoder_bwd(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
+                     const float* weight, const float* grad_out /* [n_edges] */, int dim, int apply_sigmoid,
+                     float* d_z, float* d_weight, void* ws, size_t ws_bytes, void* stream);
+/* Fused TIP loss (src/layers.py:335-340) over one edge set: scores, BCE terms and the analytic
+ * gradient in one pass.  sign=+1: positives, -mean(log(s + 1e-13)); sign=-1: negatives,
+ * -mean(log(1 - s + 1e-13)).  Outputs: loss_out[0] (scalar), d_z, d_weight = gradients of that term
+ * for an upstream gradient of 1 (accumulate=1 adds into d_z/d_weight/loss_out instead of overwriting). */
+int tipb_decoder_bce_fused(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
+                           const float* weight, int dim, int sign, int accumulate, float* loss_out, float* d_z,
+                           float* d_weight, void* ws, size_t ws_bytes, void* stream);
+/* all n_nodes^2 x n_rel scores (BASELINE.json config 5): out[r,i,j] */
+int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim,
+                       int apply_sigmoid, float* out, void* stream);
+
+/* ---------------------------------------------------------------- typed negative sampling
+ * Replaces typed_negative_sampling (src/neg_sampling.py:5-26) bit for bit, including the legacy
+ * numpy MT19937 stream behind np.random.choice, the retry loop's indexing quirk and the float32
+ * row = perm / num_nodes.  `mt_state` is [624 key words, position] = 625 uint32 on the device,
+ * interchangeable with numpy's RandomState.get_state()[1:3]; it is advanced in place.
+ * `member` is the per-relation membership bitmap of the positive pairs (tipb_neg_bitmap_build). */
+size_t tipb_neg_bitmap_bytes(int64_t n_nodes, int64_t n_rel);
+int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges,
+                          int64_t n_nodes, int64_t n_rel, uint32_t* member, void* stream);
+/* budget_words = how many fresh MT19937 words to generate for this call (an upper bound on what the
+ * rejection loops will consume; *status gets bit0 if it was too small, bit1 if a relation needed more
+ * than 64 retry rounds -- the caller then restores the state, enlarges the budget and calls again). */
+size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t budget_words);
+int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* member, const int64_t* range_list,
+                    int64_t n_edges, int64_t n_nodes, int64_t n_rel, int64_t budget_words,
+                    int64_t* neg_edge_index /* [2,n_edges] */, int32_t* status, void* ws, size_t ws_bytes,
+                    void* stream);
+int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIPB200_H */

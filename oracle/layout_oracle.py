@@ -48,13 +48,13 @@ def process_edges(rng, raw_edge_list, p=0.9):
 
 def typed_csr(edge_index, edge_type, n_nodes, n_rel, by="dst"):
     """Index structures of the CUDA path (tip_b200/csrc/typed_csr.cu), by definition:
-    stable sort of the edges by (node, relation, other endpoint) where node is the
-    target (by='dst') or the source (by='src') endpoint.
+    STABLE sort of the edges by (node, relation) -- ties keep their input order --
+    where node is the target (by='dst') or the source (by='src') endpoint.
 
     returns dict(eid, other, seg_ptr, seg_node, seg_rel, node_ptr, deg)."""
     a, b = (1, 0) if by == "dst" else (0, 1)
     node, other = edge_index[a].astype(np.int64), edge_index[b].astype(np.int64)
-    order = np.lexsort((other, edge_type, node))           # last key is primary; stable
+    order = np.lexsort((edge_type, node))                  # last key is primary; stable
     key = node[order] * n_rel + edge_type[order]
     first = np.ones(order.size, dtype=bool)
     first[1:] = key[1:] != key[:-1]

@@ -112,8 +112,9 @@ class GCNConv(MessagePassing):
         super().__init__(aggr="add", **kwargs)
         self.in_channels, self.out_channels, self.cached = in_channels, out_channels, cached
         self._cached_edge_index = None
-        self.lin = _Linear(in_channels, out_channels)
+        self.lin = _Linear(in_channels, out_channels)      # PyG's Linear.__init__ initialises itself ...
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin.reset_parameters()                         # ... and GCNConv.reset_parameters() draws it again
 
     def forward(self, x, edge_index):
         cache = self._cached_edge_index

@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/tipb200.h declares, the ctypes table matches the header, size queries work without a GPU,
+and the product refuses CPU tensors instead of falling back."""
+import os
+import re
+
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "tipb200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tipb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tip_b200 import _lib
+    handle = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in tipb200.h but not exported by libtipb200.so"
+        assert n in _lib.SIGNATURES, f"{n} declared in tipb200.h but missing from the ctypes table"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert handle.tipb_version() == 100
+
+
+def test_size_queries_need_no_gpu():
+    from tip_b200 import _lib
+    L = _lib.lib()
+    e, n, r = 8_280_000, 645, 861
+    assert L.tipb_typed_csr_bytes(e, n, r) > 4 * 2 * e
+    assert L.tipb_typed_csr_workspace_bytes(e, n, r) > 0
+    layout, cap = _lib.csr_layout(e, n, r)
+    assert cap == n * r and layout["counts"] == 0 and all(v % 256 == 0 for v in layout.values())
+    assert L.tipb_rgcn_workspace_bytes(e, n, r, 64, 32, 32) >= n * r * 64 * 4
+    assert L.tipb_neg_sample_workspace_bytes(e, r, 13_000_000) > 13_000_000 * 16
+    assert L.tipb_neg_bitmap_bytes(n, r) == ((n * n + 31) // 32) * 4 * r
+    assert L.tipb_sort_workspace_bytes(e) > 0 and L.tipb_scan_workspace_bytes(e) > 0
+
+
+def test_argument_errors_are_reported_not_thrown():
+    from tip_b200 import _lib
+    L = _lib.lib()
+    rc = L.tipb_typed_csr_build(None, None, None, 5, 10, 10, 3, 0, 0, 0, None, 0, None, 0, None)
+    assert rc == -1 and b"typed_csr_build" in L.tipb_last_error()
+
+
+def test_no_cpu_fallback():
+    from tip_b200 import TipbError, layers
+    conv = layers.MyRGCNConv2(8, 4, 3, 2, after_relu=False)
+    ei = torch.zeros((2, 4), dtype=torch.long)
+    with pytest.raises(TipbError):
+        conv(torch.randn(5, 8), ei, torch.zeros(4, dtype=torch.long), torch.tensor([[0, 4], [4, 4], [4, 4]]))
+    dec = layers.MultiInnerProductDecoder(4, 3)
+    with pytest.raises(TipbError):
+        dec(torch.randn(5, 4), ei, torch.zeros(4, dtype=torch.long))
+    with pytest.raises(TipbError):
+        layers.typed_negative_sampling(ei, 5, torch.tensor([[0, 4]]))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_init_draw_order_matches_reference_modules(golden_layers):
+    """same seed -> same parameters as the reference's own modules (values from tests/golden)."""
+    from tip_b200 import layers
+    torch.manual_seed(1111)
+    x = torch.randn(40, 24)   # make_golden.py draws x before building the conv
+    conv = layers.MyRGCNConv2(24, 12, 6, 5, after_relu=False)
+    assert torch.equal(x, torch.from_numpy(golden_layers["rgcn2/x"]))
+    for name in ("att", "root", "basis"):
+        assert torch.equal(getattr(conv, name).data, torch.from_numpy(golden_layers[f"rgcn2/{name}"])), name

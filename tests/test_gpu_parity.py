@@ -1,0 +1,376 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the drop-in modules) against
+  (1) the golden vectors dumped from the reference's own code (tests/golden, oracle/make_golden.py) and
+  (2) the CPU oracle (oracle/*.py) on seeded random inputs, in fp32 and against its fp64 evaluation.
+Integer/index work must match bit for bit; floating point within fp32 rtol 1e-4 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # BASELINE.json north_star: "within fp32 rtol 1e-4 for embeddings, logits and loss"
+ATOL_REL = 2e-6      # absolute floor, relative to the largest reference magnitude (for entries near zero)
+
+
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def close(a, b, rtol=RTOL, atol_rel=ATOL_REL, what=""):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(float(np.abs(b).max()), 1e-30) if b.size else 1.0
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_rel * scale, err_msg=what)
+
+
+def T(a, device=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t if device is None else t.to(device)
+
+
+# =============================================================================== primitives
+def test_scan_and_sort_primitives():
+    from tip_b200 import _lib
+    d = dev()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 31, 4096, 4097, 100_003, 3_000_001):
+        x = torch.randint(0, 5, (n,), generator=g, dtype=torch.int32)
+        xin = x.to(d)
+        out = torch.empty(n + 1, dtype=torch.int32, device=d)
+        ws = torch.empty(L.tipb_scan_workspace_bytes(n), dtype=torch.uint8, device=d)
+        _lib.check(L.tipb_exclusive_scan_i32(xin.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws.numel(), _lib.stream()), "scan")
+        ref = np.concatenate([[0], np.cumsum(x.numpy().astype(np.int64))])
+        assert np.array_equal(out.cpu().numpy(), ref), n
+    for n, bits in ((1, 3), (1000, 8), (70_001, 20), (1_000_003, 26), (300_000, 32), (5000, 16)):
+        keys = torch.randint(0, 2 ** bits, (n,), generator=g, dtype=torch.int64)
+        k_in = torch.from_numpy(keys.numpy().astype(np.uint32).view(np.int32)).to(d)
+        v_in = torch.arange(n, dtype=torch.int32, device=d)
+        k_out, v_out = torch.empty_like(k_in), torch.empty_like(v_in)
+        ws = torch.empty(L.tipb_sort_workspace_bytes(n), dtype=torch.uint8, device=d)
+        _lib.check(L.tipb_sort_pairs_u32(k_in.data_ptr(), v_in.data_ptr(), k_out.data_ptr(), v_out.data_ptr(), n, bits,
+                                         ws.data_ptr(), ws.numel(), _lib.stream()), "sort")
+        order = np.argsort(keys.numpy(), kind="stable")
+        assert np.array_equal(v_out.cpu().numpy(), order.astype(np.int32)), (n, bits)
+        got_keys = k_out.cpu().numpy().view(np.uint32).astype(np.int64)
+        assert np.array_equal(got_keys, keys.numpy()[order]), (n, bits)
+
+
+# =============================================================================== typed CSR (bit exact)
+def _check_plan(plan, ei, et, n, r, by, doubled=False, drop_loops=False):
+    from oracle import layout_oracle as lo
+    ei, et = np.asarray(ei), np.asarray(et)
+    e = ei.shape[1]
+    if doubled:
+        ei = np.concatenate([ei, ei[::-1]], axis=1)
+        et = np.concatenate([et, et])
+    keep = np.ones(ei.shape[1], dtype=bool)
+    if drop_loops:
+        keep = ei[0] != ei[1]
+    ids = np.nonzero(keep)[0]
+    ref = lo.typed_csr(ei[:, ids], et[ids], n, r, by=by)
+    cnt = plan.field("counts").cpu().numpy()
+    S = int(cnt[0])
+    assert S == len(ref["seg_node"]) and int(cnt[1]) == ids.size and int(cnt[2]) == 0
+    assert np.array_equal(plan.field("eid").cpu().numpy()[:ids.size], ids[ref["eid"]].astype(np.int32))
+    assert np.array_equal(plan.field("other").cpu().numpy()[:ids.size], ref["other"])
+    assert np.array_equal(plan.field("seg_ptr").cpu().numpy()[:S + 1], ref["seg_ptr"])
+    assert np.array_equal(plan.field("seg_node").cpu().numpy()[:S], ref["seg_node"])
+    assert np.array_equal(plan.field("seg_rel").cpu().numpy()[:S], ref["seg_rel"])
+    assert np.array_equal(plan.field("node_ptr").cpu().numpy(), ref["node_ptr"])
+    assert np.array_equal(plan.field("deg").cpu().numpy(), ref["deg"])
+    inv = 1.0 / np.maximum(ref["deg"], 1).astype(np.float32)
+    assert np.array_equal(plan.field("inv_deg").cpu().numpy(), inv.astype(np.float32))
+    # relation-major listing: stable by relation
+    rs = plan.field("rel_seg").cpu().numpy()[:S]
+    assert np.array_equal(rs, np.argsort(ref["seg_rel"], kind="stable").astype(np.int32))
+    rp = plan.field("rel_seg_ptr").cpu().numpy()
+    assert np.array_equal(rp, np.searchsorted(ref["seg_rel"][rs], np.arange(r + 1)).astype(np.int32))
+
+
+def test_typed_csr_bit_exact(golden_layers):
+    from tip_b200 import ops
+    d = dev()
+    g = golden_layers
+    ei, et, rl = g["data/dd_train_idx"], g["data/dd_train_et"], g["data/dd_train_range"]
+    n, r = int(g["data/n_drug"]), int(g["data/n_dd_et"])
+    for by_src in (False, True):
+        for doubled in (False, True):
+            plan = ops.TypedCSR(ei.shape[1], n, r, d, by_src=by_src, doubled=doubled).build(T(ei, d), range_list=T(rl, d))
+            _check_plan(plan, ei, et, n, r, "src" if by_src else "dst", doubled=doubled)
+            plan2 = ops.TypedCSR(ei.shape[1], n, r, d, by_src=by_src, doubled=doubled).build(T(ei, d), edge_type=T(et, d))
+            assert torch.equal(plan.buf, plan2.buf)
+    # unsorted edge types, random multigraph with self loops and duplicates, one relation unused
+    rng = np.random.default_rng(5)
+    for (n, r, e) in ((7, 3, 50), (645, 861, 200_000), (1, 1, 10), (300, 1, 5000), (50, 4, 0)):
+        ei = rng.integers(0, n, (2, e)).astype(np.int64)
+        et = rng.integers(0, max(r - 1, 1), e).astype(np.int64)
+        for by_src in (False, True):
+            plan = ops.TypedCSR(e, n, r, d, by_src=by_src, drop_self_loops=(r == 1)).build(T(ei, d), edge_type=T(et, d))
+            _check_plan(plan, ei, et, n, r, "src" if by_src else "dst", drop_loops=(r == 1))
+    # out-of-range indices are dropped and flagged, never dereferenced
+    ei = np.array([[0, 1, 9, 2], [1, -1, 0, 2]], dtype=np.int64)
+    plan = ops.TypedCSR(4, 3, 1, d).build(T(ei, d))
+    cnt = plan.field("counts").cpu().numpy()
+    assert int(cnt[2]) == 1 and int(cnt[1]) == 2
+    with pytest.raises(IndexError):
+        plan.check_status()
+
+
+# =============================================================================== operators vs golden
+def _rgcn_golden(g, pre, module_cls, d, shuffled):
+    from tip_b200 import layers
+    ei, et, rl = T(g["data/dd_train_idx"], d), T(g["data/dd_train_et"], d), T(g["data/dd_train_range"], d)
+    n_rel = int(g["data/n_dd_et"])
+    conv = module_cls(24, 12, n_rel, 5, after_relu=(pre == "rgcn1")).to(d)
+    with torch.no_grad():
+        for k in ("att", "basis", "root"):
+            getattr(conv, k).copy_(T(g[f"{pre}/{k}"], d))
+    x = T(g["rgcn2/x"], d).requires_grad_(True)
+    if shuffled:
+        perm = T(g["rgcn1/perm"], d)
+        out = conv(x, ei[:, perm].contiguous(), et[perm].contiguous())
+    else:
+        out = conv(x, ei, et, rl)
+    close(out, g[f"{pre}/out"], what=pre + " out")
+    out.backward(T(g["rgcn2/gout"], d))
+    close(x.grad, g[f"{pre}/dx"], what=pre + " dx")
+    for k in ("att", "basis", "root"):
+        close(getattr(conv, k).grad, g[f"{pre}/d_{k}"], what=f"{pre} d_{k}")
+
+
+def test_rgcn_conv2_matches_reference(golden_layers):
+    from tip_b200 import layers
+    _rgcn_golden(golden_layers, "rgcn2", layers.MyRGCNConv2, dev(), shuffled=False)
+
+
+def test_rgcn_conv_unsorted_edge_types_matches_reference(golden_layers):
+    from tip_b200 import layers
+    _rgcn_golden(golden_layers, "rgcn1", layers.MyRGCNConv, dev(), shuffled=True)
+
+
+def test_pp_encoder_matches_reference(golden_layers):
+    from tip_b200 import layers
+    d, g = dev(), golden_layers
+    n_prot = int(g["data/n_prot"])
+    pp = layers.PPEncoder(n_prot).to(d)
+    with torch.no_grad():
+        for k in ("conv1.lin.weight", "conv1.bias", "conv2.lin.weight", "conv2.bias"):
+            dict(pp.named_parameters())[k].copy_(T(g[f"pp/{k}"], d))
+    feat = layers.sparse_id(n_prot).to(d)
+    out = pp(feat, T(g["data/pp_train_indices"], d))
+    close(out, g["pp/out"], what="pp out")
+    out.backward(T(g["pp/gout"], d))
+    for k, p in pp.named_parameters():
+        close(p.grad, g[f"pp/d_{k}"], what="pp d_" + k)
+    # dense identity features take the matmul path and agree
+    out2 = pp(torch.eye(n_prot, device=d), T(g["data/pp_train_indices"], d))
+    close(out2, g["pp/out"], what="pp out (dense features)")
+
+
+def test_hierarchy_conv_matches_reference(golden_layers):
+    from tip_b200 import layers
+    d, g = dev(), golden_layers
+    n_prot, n_drug = int(g["data/n_prot"]), int(g["data/n_drug"])
+    hc = layers.MyHierarchyConv(16, 10, n_prot, n_drug).to(d)
+    with torch.no_grad():
+        hc.weight.copy_(T(g["hier/weight"], d))
+    x = T(g["hier/x"], d).requires_grad_(True)
+    out = hc(x, T(g["data/dp_edge_index"], d), None)
+    close(out, g["hier/out"], what="hier out")
+    out.backward(T(g["hier/gout"], d))
+    close(x.grad, g["hier/dx"], what="hier dx")
+    close(hc.weight.grad, g["hier/d_weight"], what="hier d_weight")
+
+
+def test_decoder_matches_reference(golden_layers):
+    from tip_b200 import layers
+    d, g = dev(), golden_layers
+    n_rel = int(g["data/n_dd_et"])
+    perm = T(g["rgcn1/perm"], d)
+    ei, et = T(g["data/dd_train_idx"], d)[:, perm].contiguous(), T(g["data/dd_train_et"], d)[perm].contiguous()
+    dec = layers.MultiInnerProductDecoder(12, n_rel).to(d)
+    with torch.no_grad():
+        dec.weight.copy_(T(g["dec/weight"], d))
+    z = T(g["dec/z"], d).requires_grad_(True)
+    close(dec(z, ei, et, sigmoid=False), g["dec/value"], what="dec value")
+    sc = dec(z, ei, et)
+    close(sc, g["dec/score"], what="dec score")
+    sc.backward(T(g["dec/gscore"], d))
+    close(z.grad, g["dec/dz"], what="dec dz")
+    close(dec.weight.grad, g["dec/d_weight"], what="dec d_weight")
+    # sweep = all pairs, every relation
+    full = dec.sweep(z.detach(), sigmoid=False)
+    zc, wc = z.detach().cpu().double(), dec.weight.detach().cpu().double()
+    ref = torch.einsum("ik,rk,jk->rij", zc, wc, zc)
+    close(full, ref, what="dec sweep")
+
+
+# =============================================================================== negative sampler (bit exact)
+def test_negative_sampling_bit_exact(golden_neg):
+    from tip_b200 import neg_sampling as ns
+    d = dev()
+    for case in ("dense37", "drug645", "big10k", "tiny1"):
+        g = {k.split("/", 1)[1]: v for k, v in golden_neg.items() if k.startswith(case + "/")}
+        ns.set_state(("MT19937", g["key0"], int(g["pos0"])), d)
+        st = ns.get_state(d)
+        assert np.array_equal(st[1], g["key0"]) and st[2] == int(g["pos0"])
+        pos, rl, n = T(g["pos"], d), T(g["range_list"], d), int(g["num_nodes"])
+        out1 = ns.typed_negative_sampling(pos, n, rl)
+        out2 = ns.typed_negative_sampling(pos, n, rl)
+        assert out1.dtype == torch.long and tuple(out1.shape) == g["neg_call1"].shape
+        assert np.array_equal(out1.cpu().numpy(), g["neg_call1"]), case + " call 1"
+        assert np.array_equal(out2.cpu().numpy(), g["neg_call2"]), case + " call 2"
+        st = ns.get_state(d)
+        assert np.array_equal(st[1], g["key_end"]) and st[2] == int(g["pos_end"]), case + " final MT state"
+
+
+def test_negative_sampling_seed_and_numpy_handover():
+    from oracle import neg_sampling_oracle as nso
+    from tip_b200 import neg_sampling as ns
+    d = dev()
+    ns.seed(1111, d)
+    rs = np.random.RandomState(1111)
+    st = ns.get_state(d)
+    assert np.array_equal(st[1], rs.get_state()[1]) and st[2] == 624
+    # tiny budget forces the out-of-words retry path; result must not change
+    rng = np.random.default_rng(1)
+    n = 101
+    pairs = rng.integers(0, n, (2, 4000)).astype(np.int64)
+    rl = np.array([[0, 1500], [1500, 1500], [1500, 4000]], dtype=np.int64)
+    mt = nso.MT19937(1111)
+    ref = nso.typed_negative_sampling(mt, pairs, n, rl)
+    pos_t, rl_t = T(pairs, d), T(rl, d)
+    m = ns._membership(pos_t, n, rl_t)
+    m.budget = 700
+    out = ns.typed_negative_sampling(pos_t, n, rl_t)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    st = ns.get_state(d)
+    assert np.array_equal(st[1], mt.key) and st[2] == mt.pos
+    # hand the stream to numpy and continue there
+    np.random.set_state(st)
+    assert np.array_equal(np.random.choice(n * n, 50), mt.choice(n * n, 50))
+
+
+# =============================================================================== whole model vs golden
+@pytest.mark.parametrize("mod", ["cat", "add"])
+def test_tip_model_matches_reference(golden_layers, mod):
+    from tip_b200 import layers, neg_sampling as ns
+    d, g = dev(), golden_layers
+    pre = f"tip_{mod}/"
+    data = {k: T(g[f"data/{k}"]) for k in ("dd_train_idx", "dd_train_et", "dd_train_range", "dd_test_idx", "dd_test_et",
+                                           "dd_test_range", "pp_train_indices", "dp_edge_index", "d_norm")}
+    n_drug, n_prot = int(g["data/n_drug"]), int(g["data/n_prot"])
+    data.update(n_drug=n_drug, n_prot=n_prot, n_dd_et=int(g["data/n_dd_et"]), n_drug_feat=n_drug,
+                d_feat=layers.sparse_id(n_drug), p_feat=layers.sparse_id(n_prot), dp_range_list=torch.zeros(n_drug, 2))
+    dims = dict(prot_drug_dim=16, n_embed=48) if mod == "cat" else dict(prot_drug_dim=64, n_embed=64)
+    settings = layers.Setting(sp_rate=0.9, lr=0.01, n_hid1=32, n_hid2=16, num_base=32, **dims)
+    torch.manual_seed(1111)
+    ns.seed(1111, d)
+    model = layers.TIP(settings, d, mod=mod, data=data)
+    # the constructor drew the test-set negatives from the stream exactly like the reference
+    assert np.array_equal(model.test_neg_index.cpu().numpy(), g[pre + "test_neg"])
+    st = ns.get_state(d)
+    assert np.array_equal(st[1], g[pre + "mt_key"]) and st[2] == int(g[pre + "mt_pos"])
+    names = [n for n, _ in model.named_parameters()]
+    assert names == [k[len(pre + "param/"):] for k in g if k.startswith(pre + "param/")]
+    # R-GCN / hierarchy / decoder / embed initial values come from the same torch seed; the GCN init of real PyG is
+    # unverifiable here so all parameters are loaded from the golden file before comparing numbers
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            p.copy_(T(g[pre + "param/" + n_], d))
+    model.train()
+    loss = model()
+    assert np.array_equal(model._neg_index.cpu().numpy(), g[pre + "neg"])
+    close(model.embeddings, g[pre + "z"], what="z")
+    close(loss, g[pre + "loss"], rtol=1e-5, what="loss")
+    loss.backward()
+    for n_, p in model.named_parameters():
+        close(p.grad, g[pre + "grad/" + n_], what="grad " + n_)
+    # three Adam steps (tip.py:21-30): same loss trajectory
+    ns.set_state(("MT19937", g[pre + "mt_key"], int(g[pre + "mt_pos"])), d)
+    opt = torch.optim.Adam(model.parameters(), lr=settings.lr)
+    traj = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = model()
+        traj.append(float(loss))
+        loss.backward()
+        opt.step()
+    close(np.array(traj), g[pre + "loss_traj"], rtol=1e-4, what="loss trajectory")
+
+
+# =============================================================================== CUDA path vs oracle, larger random inputs
+def _random_typed_graph(rng, n, r, e):
+    sizes = rng.multinomial(e, rng.dirichlet(np.ones(r) * 0.5))
+    pop = rng.lognormal(0, 1, n)
+    pop /= pop.sum()
+    ei = np.stack([rng.choice(n, e, p=pop), rng.choice(n, e, p=pop)]).astype(np.int64)
+    et = np.repeat(np.arange(r), sizes).astype(np.int64)
+    ends = np.cumsum(sizes)
+    rl = np.stack([ends - sizes, ends], axis=1).astype(np.int64)
+    return ei, et, rl
+
+
+@pytest.mark.parametrize("shape", [(645, 200, 300_000, 64, 32, 32), (333, 50, 40_000, 32, 16, 32), (97, 7, 3000, 20, 6, 3)])
+def test_rgcn_against_fp64_oracle(shape):
+    from oracle import tip_oracle as to
+    from tip_b200 import layers
+    d = dev()
+    n, r, e, fi, fo, nb = shape
+    rng = np.random.default_rng(n)
+    ei, et, rl = _random_typed_graph(rng, n, r, e)
+    torch.manual_seed(n)
+    conv = layers.MyRGCNConv2(fi, fo, r, nb, after_relu=False).to(d)
+    x = torch.randn(n, fi)
+    gout = torch.randn(n, fo)
+    xg = x.to(d).requires_grad_(True)
+    out = conv(xg, T(ei, d), T(et, d), T(rl, d))
+    out.backward(gout.to(d))
+    p64 = {k: getattr(conv, k).detach().cpu().double().requires_grad_(True) for k in ("att", "basis", "root")}
+    x64 = x.double().requires_grad_(True)
+    ref = to.rgcn_conv_vectorized(x64, T(ei), T(et), p64["att"], p64["basis"], p64["root"])
+    ref.backward(gout.double())
+    close(out, ref, what="out")
+    close(xg.grad, x64.grad, what="dx")
+    for k in p64:
+        close(getattr(conv, k).grad, p64[k].grad, what="d_" + k)
+    # fused ReLU epilogue == relu(conv)
+    out_r = conv(xg.detach(), T(ei, d), T(et, d), T(rl, d), _fused_relu=True)
+    assert torch.equal(out_r, torch.relu(out.detach()))
+
+
+def test_bce_loss_against_oracle():
+    from oracle import tip_oracle as to
+    from tip_b200 import ops
+    d = dev()
+    rng = np.random.default_rng(3)
+    n, r, e, dim = 645, 120, 150_000, 16
+    ei, et, rl = _random_typed_graph(rng, n, r, e)
+    neg = rng.integers(0, n, (2, e)).astype(np.int64)
+    torch.manual_seed(3)
+    z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
+    zg, wg = z.to(d).requires_grad_(True), w.to(d).requires_grad_(True)
+    plan_pos = ops.TypedCSR(e, n, r, d, doubled=True).build(T(ei, d), range_list=T(rl, d))
+    plan_neg = ops.TypedCSR(e, n, r, d, doubled=True).build(T(neg, d), range_list=T(rl, d))
+    loss = ops.bce_loss(zg, wg, plan_pos, plan_neg)
+    (loss * 1.5).backward()
+    z64, w64 = z.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = to.tip_loss(to.decoder(z64, T(ei), T(et), w64), to.decoder(z64, T(neg), T(et), w64))
+    (ref * 1.5).backward()
+    close(loss, ref, rtol=1e-5, what="loss")
+    close(zg.grad, z64.grad, what="dz")
+    close(wg.grad, w64.grad, what="dw")
+    # saturated scores: the 1e-13 epsilon decides the value exactly as in the reference (fp32)
+    zs = torch.full((4, 16), 6.0)
+    ws = torch.ones(1, 16)
+    e2 = np.array([[0, 1], [2, 3]], dtype=np.int64)
+    rl2 = np.array([[0, 2]], dtype=np.int64)
+    p2 = ops.TypedCSR(2, 4, 1, d, doubled=True).build(T(e2, d), range_list=T(rl2, d))
+    l_gpu = ops.bce_loss(zs.to(d), ws.to(d), p2, p2)
+    et2 = torch.zeros(2, dtype=torch.long)
+    l_ref = to.tip_loss(to.decoder(zs, T(e2), et2, ws), to.decoder(zs, T(e2), et2, ws))
+    close(l_gpu, l_ref, rtol=1e-6, what="saturated loss")

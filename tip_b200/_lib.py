@@ -1,0 +1,100 @@
+"""ctypes binding of libtipb200.so (the C ABI declared in include/tipb200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this
+module raises.  Pointers are passed as raw device addresses (`tensor.data_ptr()`)
+and the stream is torch's current CUDA stream, so calls are CUDA-graph capturable.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtipb200.so")
+
+_p, _i64, _i32, _sz, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_uint32
+
+# name -> (restype, argtypes); mirrors include/tipb200.h one to one
+SIGNATURES = {
+    "tipb_version": (C.c_int, []),
+    "tipb_last_error": (C.c_char_p, []),
+    "tipb_scan_workspace_bytes": (_sz, [_i64]),
+    "tipb_exclusive_scan_i32": (C.c_int, [_p, _p, _i64, _p, _sz, _p]),
+    "tipb_sort_workspace_bytes": (_sz, [_i64]),
+    "tipb_sort_pairs_u32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _sz, _p]),
+    "tipb_typed_csr_bytes": (_sz, [_i64, _i64, _i64]),
+    "tipb_typed_csr_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "tipb_typed_csr_layout": (C.c_int, [_i64, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "tipb_typed_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p, _sz, _p]),
+    "tipb_rgcn_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i32]),
+    "tipb_rgcn_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_rgcn_bwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32,
+                                _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "tipb_gcn_norm": (C.c_int, [_p, _i64, _i64, _p, _p]),
+    "tipb_gcn_spmm": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _p, _p]),
+    "tipb_hier_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "tipb_hier_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _i32, _p, _p, _p]),
+    "tipb_hier_bwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_decoder_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _p]),
+    "tipb_decoder_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "tipb_decoder_bwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_decoder_bce_fused": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
+    "tipb_decoder_sweep": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
+    "tipb_neg_bitmap_bytes": (_sz, [_i64, _i64]),
+    "tipb_neg_bitmap_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "tipb_neg_sample_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "tipb_neg_sample": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "tipb_mt19937_seed": (C.c_int, [_p, _u32, _p]),
+}
+
+CSR_FIELDS = ("counts", "eid", "other", "seg_ptr", "seg_node", "seg_rel", "node_ptr", "deg", "inv_deg",
+              "rel_seg_ptr", "rel_seg")
+
+_lib = None
+
+
+class TipbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TipbError(
+                f"{LIB_PATH} not found: build it with `make -C tip_b200/csrc` (or __graft_entry__.build()). "
+                "tip_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise TipbError(f"{what} failed (code {rc}): {lib().tipb_last_error().decode()}")
+
+
+def ptr(t):
+    """device address of a tensor (None -> NULL); requires a contiguous CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TipbError("tip_b200 operators take CUDA tensors only (there is no CPU path)")
+    if not t.is_contiguous():
+        raise TipbError("internal error: non-contiguous tensor reached the C ABI")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def csr_layout(n_entries, n_nodes, n_rel):
+    offs = (_i64 * len(CSR_FIELDS))()
+    cap = _i64()
+    check(lib().tipb_typed_csr_layout(n_entries, n_nodes, n_rel, offs, C.byref(cap)), "typed_csr_layout")
+    return dict(zip(CSR_FIELDS, list(offs))), cap.value

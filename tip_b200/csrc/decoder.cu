@@ -1,0 +1,363 @@
+// DistMult decoder (reference src/layers.py:581-595), the TIP loss (src/layers.py:335-340) and
+// their gradients (north_star item 4: fused gather-bilinear-sigmoid-BCE).
+//
+//   value_e = sum_k z[i_e,k] z[j_e,k] w[r_e,k]        score_e = sigmoid(value_e)
+//   loss    = -mean(log(score_pos + 1e-13)) - mean(log(1 - score_neg + 1e-13))
+//
+// The gradient with respect to z is a scatter over BOTH endpoints of every pair.  To keep it free
+// of atomics, every edge set is indexed by a *doubled* typed CSR: each pair (i,j,r) is listed under
+// (node i, relation r) with other=j and again under (node j, relation r) with other=i.  One warp
+// owns one (node, relation) segment: u = z[node] * w[rel] is loop-invariant, each entry costs one
+// 64-byte gather of z[other] (from shared memory), one dot product, and -- for the fused loss -- the
+// sigmoid/log/derivative evaluated ONCE per entry with all 32 lanes busy (entries are processed 32 at
+// a time; the per-entry scalars are transposed across the warp with shuffles).  The segment leaves
+//   acc[s,:] = sum_e g_e z[other_e,:]
+// from which  d_z[n] = sum_{s in node n} w[rel_s] * acc[s]   (node-major reduction) and
+//             d_w[r] = 1/2 sum_{s: rel_s = r} z[node_s] * acc[s]   (relation-major reduction; every pair
+//                                                                 was visited from both ends).
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace tipb {
+
+constexpr float TIP_EPS = 1e-13f;  // reference src/layers.py:15
+
+enum { DEC_MODE_POS = 0, DEC_MODE_NEG = 1, DEC_MODE_GRAD = 2 };
+
+__device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------------
+// plain forward in the caller's edge order (the module's public forward)
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_decoder_fwd(const float4* __restrict__ z, const float4* __restrict__ w, const int64_t* __restrict__ edge_index,
+              const int64_t* __restrict__ edge_type, int64_t n_edges, int n_nodes, int n_rel, int apply_sigmoid,
+              float* __restrict__ out) {
+    constexpr int G = 32 / LPR;
+    const int lane = lane_id(), g = lane / LPR, l = lane % LPR;
+    const int64_t n_groups = (int64_t(gridDim.x) * blockDim.x) / LPR;
+    for (int64_t e = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LPR; e < ((n_edges + G - 1) / G) * G;
+         e += n_groups) {
+        const bool ok = e < n_edges;
+        float p = 0.f;
+        if (ok) {
+            int64_t i = edge_index[e], j = edge_index[n_edges + e], r = edge_type[e];
+            bool in = i >= 0 && i < n_nodes && j >= 0 && j < n_nodes && r >= 0 && r < n_rel;
+            if (in) {
+                float4 a = z[i * LPR + l], b = z[j * LPR + l], c = w[r * LPR + l];
+                p = (a.x * b.x) * c.x + (a.y * b.y) * c.y + (a.z * b.z) * c.z + (a.w * b.w) * c.w;
+            } else {
+                p = __int_as_float(0x7fc00000);  // NaN marks an out-of-range index
+            }
+        }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+        if (ok && l == 0) out[e] = apply_sigmoid ? sigmoidf_ref(p) : p;
+    }
+    (void)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment kernel.  smem: z [n_nodes * LPR] float4
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(512)
+k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ seg_rel,
+              const int* __restrict__ other, const int* __restrict__ eid, const int* __restrict__ counts,
+              const float4* __restrict__ z, const float4* __restrict__ w, const float* __restrict__ grad_out,
+              int n_nodes, int n_edges, int apply_sigmoid, float inv_count, float4* __restrict__ acc_seg,
+              float4* __restrict__ zacc_seg, float* __restrict__ loss_part) {
+    extern __shared__ float4 s_z[];
+    constexpr int G = 32 / LPR;
+    const int lane = lane_id(), g = lane / LPR, l = lane % LPR;
+    for (int i = threadIdx.x; i < n_nodes * LPR; i += blockDim.x) s_z[i] = z[i];
+    __syncthreads();
+
+    const int S = counts[TIPB_CSR_COUNT_SEGMENTS];
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float loss = 0.f;
+
+    for (int s = warp_global; s < S; s += n_warps) {
+        const int beg = seg_ptr[s], end = seg_ptr[s + 1];
+        const int node = seg_node[s], rel = seg_rel[s];
+        const float4 zn = s_z[node * LPR + l];
+        const float4 wr = w[rel * LPR + l];
+        const float4 u = make_float4(zn.x * wr.x, zn.y * wr.y, zn.z * wr.z, zn.w * wr.w);
+        float4 acc = f4_zero();
+
+        for (int base = beg; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            const int my = base + lane;
+            const int idx = my < end ? ld_stream_i32(other + my) : 0;
+            float go = 0.f;
+            if (MODE == DEC_MODE_GRAD && my < end) {
+                int id = eid[my];
+                go = grad_out[id >= n_edges ? id - n_edges : id];
+            }
+            // phase A: one dot product per entry, entry k handled by group k % G in round k / G
+            float4 zj[LPR];     // LPR == number of rounds: 32 / G
+            float vmine = 0.f;  // value of entry `lane`
+#pragma unroll
+            for (int r = 0; r < LPR; ++r) {
+                const int k = r * G + g;
+                const int j = __shfl_sync(FULL, idx, k);
+                zj[r] = s_z[j * LPR + l];
+                float p = (u.x * zj[r].x + u.y * zj[r].y) + (u.z * zj[r].z + u.w * zj[r].w);
+#pragma unroll
+                for (int o = LPR >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+                // entry k's value sits on every lane of group g; lane k fetches it from lane (k % G) * LPR
+                const float pv = __shfl_sync(FULL, p, (lane % G) * LPR);
+                if (lane / G == r) vmine = pv;
+            }
+            // phase B: all 32 lanes evaluate the scalar chain of their own entry
+            float gmine = 0.f;
+            if (lane < cnt) {
+                if (MODE == DEC_MODE_GRAD) {
+                    if (apply_sigmoid) {
+                        const float sg = sigmoidf_ref(vmine);
+                        gmine = go * sg * (1.f - sg);
+                    } else {
+                        gmine = go;
+                    }
+                } else {
+                    const float sg = sigmoidf_ref(vmine);
+                    if (MODE == DEC_MODE_POS) {
+                        loss -= logf(sg + TIP_EPS);
+                        gmine = -(sg * (1.f - sg)) / (sg + TIP_EPS) * inv_count;
+                    } else {
+                        const float om = 1.f - sg;
+                        loss -= logf(om + TIP_EPS);
+                        gmine = (sg * om) / (om + TIP_EPS) * inv_count;
+                    }
+                }
+            }
+            // phase C: acc += g_e * z[other_e]
+#pragma unroll
+            for (int r = 0; r < LPR; ++r) {
+                const float ge = __shfl_sync(FULL, gmine, r * G + g);
+                acc = f4_fma(ge, zj[r], acc);
+            }
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            acc.x += __shfl_xor_sync(FULL, acc.x, o);
+            acc.y += __shfl_xor_sync(FULL, acc.y, o);
+            acc.z += __shfl_xor_sync(FULL, acc.z, o);
+            acc.w += __shfl_xor_sync(FULL, acc.w, o);
+        }
+        if (g == 0) {
+            acc_seg[int64_t(s) * LPR + l] = make_float4(acc.x * wr.x, acc.y * wr.y, acc.z * wr.z, acc.w * wr.w);
+            zacc_seg[int64_t(s) * LPR + l] = make_float4(acc.x * zn.x, acc.y * zn.y, acc.z * zn.z, acc.w * zn.w);
+        }
+    }
+    if (MODE != DEC_MODE_GRAD) {
+        loss = warp_sum(loss);
+        if (lane == 0) loss_part[warp_global] = loss;
+    }
+}
+
+// d_z[n, :] (+)= sum_{s in node n} wacc_seg[s, :]
+__global__ void __launch_bounds__(128)
+k_decoder_node_reduce(const int* __restrict__ node_ptr, const float* __restrict__ wacc_seg, int dim, int accumulate,
+                      float* __restrict__ d_z) {
+    __shared__ float part[128];
+    const int n = blockIdx.x;
+    const int sb = node_ptr[n], se = node_ptr[n + 1];
+    const int per = 128 / dim;  // dim <= 128 and a power of two
+    const int k = threadIdx.x % dim, sg = threadIdx.x / dim;
+    float a = 0.f;
+    for (int s = sb + sg; s < se; s += per) a += wacc_seg[int64_t(s) * dim + k];
+    part[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < dim) {
+        float t = 0.f;
+        for (int q = 0; q < per; ++q) t += part[q * dim + threadIdx.x];
+        float* dst = d_z + int64_t(n) * dim + threadIdx.x;
+        *dst = accumulate ? *dst + t : t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_loss_reduce(const float* __restrict__ loss_part, int n, float scale, int accumulate, float* __restrict__ loss_out) {
+    __shared__ float sw[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) a += loss_part[i];
+    a = warp_sum(a);
+    if (lane_id() == 0) sw[warp_id()] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t += sw[w];
+        t *= scale;
+        loss_out[0] = accumulate ? loss_out[0] + t : t;
+    }
+}
+
+__global__ void k_add_inplace(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+// full sweep: out[r, i, j] = act( sum_k z[i,k] w[r,k] z[j,k] )     (BASELINE.json config 5)
+__global__ void __launch_bounds__(256)
+k_decoder_sweep(const float* __restrict__ z, const float* __restrict__ w, int n_nodes, int dim, int apply_sigmoid,
+                float* __restrict__ out) {
+    extern __shared__ float sm[];  // u [8][dim] for this CTA's 8 rows i
+    const int r = blockIdx.y;
+    const int i0 = blockIdx.x * 8;
+    for (int t = threadIdx.x; t < 8 * dim; t += blockDim.x) {
+        int ii = i0 + t / dim, k = t % dim;
+        sm[t] = ii < n_nodes ? z[int64_t(ii) * dim + k] * w[int64_t(r) * dim + k] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_nodes; j += blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < dim; ++k) {
+            const float zj = z[int64_t(j) * dim + k];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = fmaf(sm[q * dim + k], zj, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int ii = i0 + q;
+            if (ii < n_nodes) {
+                float v = acc[q];
+                if (apply_sigmoid) v = 1.0f / (1.0f + __expf(-v));
+                out[(int64_t(r) * n_nodes + ii) * n_nodes + j] = v;
+            }
+        }
+    }
+}
+
+static int dec_seg_grid() { return sm_count() * 2; }
+
+struct DecWs { float *acc_seg, *zacc_seg, *loss_part, *dw_tmp; };
+static size_t dec_ws_bytes(int64_t seg_cap, int64_t n_rel, int dim) {
+    return (2 * size_t(seg_cap) * dim + size_t(dec_seg_grid()) * 16 + size_t(n_rel) * dim) * 4 + 2048;
+}
+
+template <int LPR>
+static int decoder_seg_run(const CsrView& v, int mode, const float* z, const float* w, const float* grad_out,
+                           int64_t n_edges, int apply_sigmoid, int accumulate, float* loss_out, float* d_z,
+                           float* d_w, void* ws, cudaStream_t s) {
+    const int dim = LPR * 4;
+    Carver c(ws);
+    float* acc_seg = c.take<float>(size_t(v.seg_cap) * dim);
+    float* zacc_seg = c.take<float>(size_t(v.seg_cap) * dim);
+    const int grid = dec_seg_grid();
+    const int n_warps = grid * 16;
+    float* loss_part = c.take<float>(n_warps);
+    float* dw_tmp = c.take<float>(size_t(v.n_rel) * dim);
+    const size_t smem = size_t(v.n_nodes) * dim * sizeof(float);
+    const float inv_count = n_edges > 0 ? 1.0f / float(n_edges) : 0.f;
+    int rc;
+#define RUN(MODEV)                                                                                                  \
+    {                                                                                                               \
+        auto kern = k_decoder_seg<LPR, MODEV>;                                                                      \
+        if ((rc = ensure_dyn_smem((const void*)kern, smem))) return rc;                                             \
+        kern<<<grid, 512, smem, s>>>(v.seg_ptr, v.seg_node, v.seg_rel, v.other, v.eid, v.counts, (const float4*)z,  \
+                                     (const float4*)w, grad_out, (int)v.n_nodes, (int)n_edges, apply_sigmoid,       \
+                                     inv_count, (float4*)acc_seg, (float4*)zacc_seg, loss_part);                    \
+    }
+    if (mode == DEC_MODE_POS) RUN(DEC_MODE_POS)
+    else if (mode == DEC_MODE_NEG) RUN(DEC_MODE_NEG)
+    else RUN(DEC_MODE_GRAD)
+#undef RUN
+    k_decoder_node_reduce<<<(unsigned)v.n_nodes, 128, 0, s>>>(v.node_ptr, acc_seg, dim, accumulate, d_z);
+    if (accumulate) {
+        k_rel_reduce<<<(unsigned)v.n_rel, 128, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, dw_tmp);
+        k_add_inplace<<<(unsigned)ceil_div(v.n_rel * dim, 256), 256, 0, s>>>(d_w, dw_tmp, v.n_rel * dim);
+    } else {
+        k_rel_reduce<<<(unsigned)v.n_rel, 128, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, d_w);
+    }
+    if (mode != DEC_MODE_GRAD)
+        k_loss_reduce<<<1, 1024, 0, s>>>(loss_part, n_warps, 0.5f * inv_count, accumulate, loss_out);
+    TIPB_CHECK_LAUNCH("decoder_seg");
+    return TIPB_OK;
+}
+
+static int decoder_seg_dispatch(const void* plan, int mode, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                                const float* z, const float* w, const float* grad_out, int dim, int apply_sigmoid,
+                                int accumulate, float* loss_out, float* d_z, float* d_w, void* ws, size_t ws_bytes,
+                                cudaStream_t s) {
+    CsrView v = csr_view(plan, 2 * n_edges, n_nodes, n_rel);
+    TIPB_CHECK_ARG(ws_bytes >= dec_ws_bytes(v.seg_cap, n_rel, dim), "decoder: workspace too small");
+    TIPB_CHECK_ARG(size_t(n_nodes) * dim * 4 + 1024 <= size_t(max_smem_optin()),
+                   "decoder: z (%lld x %d) does not fit in shared memory", (long long)n_nodes, dim);
+    switch (dim) {
+        case 4: return decoder_seg_run<1>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
+        case 8: return decoder_seg_run<2>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
+        case 16: return decoder_seg_run<4>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
+        case 32: return decoder_seg_run<8>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
+    }
+    set_last_error("decoder: dim=%d not in {4,8,16,32} (the Python layer pads)", dim);
+    return TIPB_ERR_UNSUPPORTED;
+}
+
+}  // namespace tipb
+
+using namespace tipb;
+
+extern "C" {
+
+int tipb_decoder_fwd(const float* z, const float* weight, const int64_t* edge_index, const int64_t* edge_type,
+                     int64_t n_edges, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid, float* out,
+                     void* stream) {
+    TIPB_CHECK_ARG(z && weight && out && (n_edges == 0 || (edge_index && edge_type)), "decoder_fwd: NULL argument");
+    if (n_edges == 0) return TIPB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = sm_count() * 8;
+#define FWD(LPRV)                                                                                                  \
+    k_decoder_fwd<LPRV><<<blocks, 256, 0, s>>>((const float4*)z, (const float4*)weight, edge_index, edge_type, n_edges, \
+                                               (int)n_nodes, (int)n_rel, apply_sigmoid, out)
+    switch (dim) {
+        case 4: FWD(1); break;
+        case 8: FWD(2); break;
+        case 16: FWD(4); break;
+        case 32: FWD(8); break;
+        case 64: FWD(16); break;
+        case 128: FWD(32); break;
+        default:
+            set_last_error("decoder_fwd: dim=%d not in {4,...,128}", dim);
+            return TIPB_ERR_UNSUPPORTED;
+    }
+#undef FWD
+    TIPB_CHECK_LAUNCH("decoder_fwd");
+    return TIPB_OK;
+}
+
+size_t tipb_decoder_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t n_rel, int dim) {
+    int64_t cap = n_nodes * n_rel, ent = 2 * n_edges;
+    int64_t seg_cap = ent < cap ? ent : cap;
+    if (seg_cap < 1) seg_cap = 1;
+    return dec_ws_bytes(seg_cap, n_rel, dim);
+}
+
+int tipb_decoder_bwd(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
+                     const float* weight, const float* grad_out, int dim, int apply_sigmoid, float* d_z,
+                     float* d_weight, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(plan_doubled && z && weight && grad_out && d_z && d_weight && ws, "decoder_bwd: NULL argument");
+    return decoder_seg_dispatch(plan_doubled, DEC_MODE_GRAD, n_edges, n_nodes, n_rel, z, weight, grad_out, dim,
+                                apply_sigmoid, 0, nullptr, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int tipb_decoder_bce_fused(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
+                           const float* weight, int dim, int sign, int accumulate, float* loss_out, float* d_z,
+                           float* d_weight, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(plan_doubled && z && weight && loss_out && d_z && d_weight && ws, "decoder_bce_fused: NULL argument");
+    TIPB_CHECK_ARG(sign == 1 || sign == -1, "decoder_bce_fused: sign must be +1 (positives) or -1 (negatives)");
+    return decoder_seg_dispatch(plan_doubled, sign > 0 ? DEC_MODE_POS : DEC_MODE_NEG, n_edges, n_nodes, n_rel, z, weight,
+                                nullptr, dim, 1, accumulate, loss_out, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid,
+                       float* out, void* stream) {
+    TIPB_CHECK_ARG(z && weight && out, "decoder_sweep: NULL argument");
+    TIPB_CHECK_ARG(dim >= 1 && dim <= 1024 && n_rel <= 65535, "decoder_sweep: dim/n_rel out of range");
+    dim3 grid((unsigned)ceil_div(n_nodes, 8), (unsigned)n_rel);
+    k_decoder_sweep<<<grid, 256, 8 * dim * sizeof(float), (cudaStream_t)stream>>>(z, weight, (int)n_nodes, dim,
+                                                                                  apply_sigmoid, out);
+    TIPB_CHECK_LAUNCH("decoder_sweep");
+    return TIPB_OK;
+}
+}

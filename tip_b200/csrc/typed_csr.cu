@@ -1,0 +1,299 @@
+// GPU-side construction of the "typed CSR" every graph kernel in this library consumes
+// (north_star item 6: CSR-by-relation construction on the GPU).
+//
+// Input is the reference's edge layout: int64 edge_index [2,E] plus either
+// an int64 edge_type [E] (MyRGCNConv, src/layers.py:76-79: any order) or the int64 range_list [R,2]
+// of relation-sorted edges (MyRGCNConv2, src/layers.py:157-160; src/utils.py:26-32).
+//
+// Output ("plan", one caller-owned device buffer; field offsets from tipb_typed_csr_layout):
+//   entries are grouped by (node, relation) -- node = target endpoint (by_src=0) or source
+//   endpoint (by_src=1) -- and keep their input order inside a group (stable sort), so every
+//   downstream floating-point sum has ONE fixed order: no atomics, run-to-run deterministic.
+//     eid[p]      input position of the p-th entry            other[p]   its opposite endpoint
+//     seg_ptr[s]  first entry of non-empty segment s          seg_node/seg_rel[s]
+//     node_ptr[n] first segment of node n                     deg/inv_deg[n]  = #entries, 1/max(#,1)
+//     rel_seg_ptr[r], rel_seg[]  the same segments listed relation-major (for per-relation reductions)
+//   `doubled=1` lists every edge in both directions (2E entries; entry e+E is edge e reversed): the
+//   decoder's symmetric score makes d(loss)/dz a sum over both endpoints of every pair.
+#include "common.cuh"
+
+namespace tipb {
+
+struct CsrLayout {
+    int64_t entries, n_nodes, n_rel, seg_cap;
+    int64_t off[TIPB_CSR_NFIELDS];
+    int64_t total_bytes;
+};
+
+static CsrLayout make_layout(int64_t entries, int64_t n_nodes, int64_t n_rel) {
+    CsrLayout L;
+    L.entries = entries;
+    L.n_nodes = n_nodes;
+    L.n_rel = n_rel;
+    int64_t cap = n_nodes * n_rel;
+    L.seg_cap = entries < cap ? entries : cap;
+    if (L.seg_cap < 1) L.seg_cap = 1;
+    int64_t counts[TIPB_CSR_NFIELDS];
+    counts[TIPB_CSR_COUNTS] = 16;
+    counts[TIPB_CSR_EID] = entries;
+    counts[TIPB_CSR_OTHER] = entries;
+    counts[TIPB_CSR_SEG_PTR] = L.seg_cap + 1;
+    counts[TIPB_CSR_SEG_NODE] = L.seg_cap;
+    counts[TIPB_CSR_SEG_REL] = L.seg_cap;
+    counts[TIPB_CSR_NODE_PTR] = n_nodes + 1;
+    counts[TIPB_CSR_DEG] = n_nodes;
+    counts[TIPB_CSR_INV_DEG] = n_nodes;
+    counts[TIPB_CSR_REL_SEG_PTR] = n_rel + 1;
+    counts[TIPB_CSR_REL_SEG] = L.seg_cap;
+    int64_t off = 0;
+    for (int f = 0; f < TIPB_CSR_NFIELDS; ++f) {
+        L.off[f] = off;
+        off += ((counts[f] > 0 ? counts[f] : 1) * 4 + 255) & ~int64_t(255);
+    }
+    L.total_bytes = off;
+    return L;
+}
+
+CsrView csr_view(const void* plan, int64_t entries, int64_t n_nodes, int64_t n_rel) {
+    CsrLayout L = make_layout(entries, n_nodes, n_rel);
+    const char* b = static_cast<const char*>(plan);
+    CsrView v;
+    v.entries = entries;
+    v.n_nodes = n_nodes;
+    v.n_rel = n_rel;
+    v.seg_cap = L.seg_cap;
+    v.counts = (int*)(b + L.off[TIPB_CSR_COUNTS]);
+    v.eid = (int*)(b + L.off[TIPB_CSR_EID]);
+    v.other = (int*)(b + L.off[TIPB_CSR_OTHER]);
+    v.seg_ptr = (int*)(b + L.off[TIPB_CSR_SEG_PTR]);
+    v.seg_node = (int*)(b + L.off[TIPB_CSR_SEG_NODE]);
+    v.seg_rel = (int*)(b + L.off[TIPB_CSR_SEG_REL]);
+    v.node_ptr = (int*)(b + L.off[TIPB_CSR_NODE_PTR]);
+    v.deg = (int*)(b + L.off[TIPB_CSR_DEG]);
+    v.inv_deg = (float*)(b + L.off[TIPB_CSR_INV_DEG]);
+    v.rel_seg_ptr = (int*)(b + L.off[TIPB_CSR_REL_SEG_PTR]);
+    v.rel_seg = (int*)(b + L.off[TIPB_CSR_REL_SEG]);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. keys: key = node * R + rel (sentinel N*R for dropped / out-of-range entries), val = entry id
+__global__ void k_csr_keys(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
+                           const int64_t* __restrict__ range_list, int64_t E, int64_t entries, int n_nodes,
+                           int n_other, int n_rel, int by_src, int drop_loops, uint32_t* __restrict__ keys,
+                           uint32_t* __restrict__ vals, int* __restrict__ counts) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= entries) return;
+    int64_t e = p < E ? p : p - E;
+    bool rev = p >= E;
+    int64_t a = edge_index[e], b = edge_index[E + e];  // a = row 0 (source), b = row 1 (target)
+    int64_t node = (by_src != 0) != rev ? a : b;
+    int64_t other = (by_src != 0) != rev ? b : a;
+    int64_t rel = 0;
+    if (edge_type) {
+        rel = edge_type[e];
+    } else if (range_list) {
+        // relation whose [start,end) holds e: last r with start <= e (ranges are cumulative)
+        int lo = 0, hi = n_rel - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (range_list[2 * mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        rel = lo;
+        // skip over empty trailing ranges that share the same start
+        if (!(range_list[2 * rel] <= e && e < range_list[2 * rel + 1])) {
+            rel = -1;
+            for (int r = lo; r >= 0 && range_list[2 * r] == range_list[2 * lo]; --r)
+                if (e < range_list[2 * r + 1]) { rel = r; break; }
+        }
+    }
+    bool ok = node >= 0 && node < n_nodes && other >= 0 && other < n_other && rel >= 0 && rel < n_rel;
+    if (!ok) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 1);
+    bool keep = ok && !(drop_loops && node == other);
+    keys[p] = keep ? uint32_t(node * n_rel + rel) : uint32_t(int64_t(n_nodes) * n_rel);
+    vals[p] = uint32_t(p);
+}
+
+// 2. after the sort: other endpoint per entry + segment-start flags
+__global__ void k_csr_flags(const int64_t* __restrict__ edge_index, int64_t E, int64_t entries, int by_src,
+                            uint32_t sentinel, const uint32_t* __restrict__ keys, const int* __restrict__ eid,
+                            int* __restrict__ other, int* __restrict__ flags) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= entries) return;
+    uint32_t k = keys[p];
+    int id = eid[p];
+    int64_t e = id < E ? id : id - E;
+    bool rev = id >= E;
+    int row = ((by_src != 0) != rev) ? 1 : 0;  // row holding the OTHER endpoint
+    other[p] = k == sentinel ? 0 : int(edge_index[int64_t(row) * E + e]);
+    flags[p] = (k != sentinel && (p == 0 || keys[p - 1] != k)) ? 1 : 0;
+}
+
+// 3. segment table from the scanned flags
+__global__ void k_csr_segments(int64_t entries, uint32_t sentinel, int n_rel, int64_t seg_cap,
+                               const uint32_t* __restrict__ keys, const int* __restrict__ seg_index /*excl scan*/,
+                               int* __restrict__ seg_ptr, int* __restrict__ seg_node, int* __restrict__ seg_rel,
+                               int* __restrict__ counts) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p > entries) return;
+    if (p == entries) {  // one past: close the last segment, publish S
+        int S = seg_index[entries];
+        counts[TIPB_CSR_COUNT_SEGMENTS] = S;
+        return;
+    }
+    uint32_t k = keys[p];
+    bool start = k != sentinel && (p == 0 || keys[p - 1] != k);
+    if (start) {
+        int s = seg_index[p];
+        seg_ptr[s] = int(p);
+        seg_node[s] = int(k / uint32_t(n_rel));
+        seg_rel[s] = int(k % uint32_t(n_rel));
+    }
+    // first dropped entry (or the end) terminates the valid range
+    bool last_valid = k != sentinel && (p + 1 == entries || keys[p + 1] == sentinel);
+    if (last_valid) {
+        int S = seg_index[p] + (start ? 1 : 0);
+        // seg_index is exclusive: segments started strictly before p, plus p's own start
+        seg_ptr[S] = int(p + 1);
+        counts[TIPB_CSR_COUNT_VALID] = int(p + 1);
+    }
+    if (p == 0 && k == sentinel) {  // nothing valid at all
+        seg_ptr[0] = 0;
+        counts[TIPB_CSR_COUNT_VALID] = 0;
+    }
+}
+
+// pad the unused tail of the per-segment tables with sentinels so host-sized launches stay simple
+__global__ void k_csr_pad(int64_t seg_cap, int n_nodes, int n_rel, const int* __restrict__ counts,
+                          int* __restrict__ seg_node, int* __restrict__ seg_rel, uint32_t* __restrict__ rkeys,
+                          uint32_t* __restrict__ rvals) {
+    int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s >= seg_cap) return;
+    int S = counts[TIPB_CSR_COUNT_SEGMENTS];
+    if (s >= S) {
+        seg_node[s] = n_nodes;
+        seg_rel[s] = n_rel;
+    }
+    rkeys[s] = uint32_t(seg_rel[s]);
+    rvals[s] = uint32_t(s);
+}
+
+// group_ptr[g] = first index i with sorted_keys[i] >= g, for g in [0, n_groups]
+template <typename K>
+__global__ void k_group_ptr(const K* __restrict__ sorted_keys, int64_t n, int n_groups, int* __restrict__ ptr) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t prev = i == 0 ? -1 : int64_t(sorted_keys[i - 1]);
+    int64_t cur = i == n ? int64_t(n_groups) : int64_t(sorted_keys[i]);
+    if (prev > n_groups) prev = n_groups;
+    if (cur > n_groups) cur = n_groups;
+    for (int64_t g = prev + 1; g <= cur; ++g) ptr[g] = int(i);
+}
+
+__global__ void k_csr_degrees(int n_nodes, const int* __restrict__ node_ptr, const int* __restrict__ seg_ptr,
+                              int* __restrict__ deg, float* __restrict__ inv_deg) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    int d = seg_ptr[node_ptr[n + 1]] - seg_ptr[node_ptr[n]];
+    deg[n] = d;
+    inv_deg[n] = 1.0f / float(d < 1 ? 1 : d);
+}
+
+__global__ void k_copy_u32_to_i32(const uint32_t* __restrict__ in, int* __restrict__ out, int64_t n) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = int(in[i]);
+}
+
+static int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 32 && (uint64_t(1) << b) <= max_value) ++b;
+    return b;
+}
+
+size_t csr_build_ws_bytes(int64_t entries, int64_t n_nodes, int64_t n_rel) {
+    CsrLayout L = make_layout(entries, n_nodes, n_rel);
+    int64_t m = entries > L.seg_cap ? entries : L.seg_cap;
+    size_t arrays = 5 * (((m + 1) * 4 + 255) & ~size_t(255));
+    return arrays + sort_ws_bytes(m) + scan_ws_bytes(m + 1) + 1024;
+}
+
+int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list, int64_t E,
+              int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled, int drop_loops, void* plan,
+              void* ws, cudaStream_t s) {
+    const int64_t entries = doubled ? 2 * E : E;
+    CsrView v = csr_view(plan, entries, n_nodes, n_rel);
+    const uint32_t sentinel = uint32_t(n_nodes * n_rel);
+    const int T = 256;
+    int64_t m = entries > v.seg_cap ? entries : v.seg_cap;
+    Carver c(ws);
+    uint32_t* k0 = c.take<uint32_t>(m + 1);
+    uint32_t* v0 = c.take<uint32_t>(m + 1);
+    uint32_t* k1 = c.take<uint32_t>(m + 1);
+    uint32_t* v1 = c.take<uint32_t>(m + 1);
+    int* flags = c.take<int>(m + 1);
+    void* sort_ws = c.take<char>(sort_ws_bytes(m));
+    void* scan_ws = c.take<char>(scan_ws_bytes(m + 1));
+
+    TIPB_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, 16 * sizeof(int), s));
+    TIPB_CHECK_CUDA(cudaMemsetAsync(v.seg_ptr, 0, (v.seg_cap + 1) * sizeof(int), s));
+    int rc;
+    if (entries > 0) {
+        unsigned g = (unsigned)ceil_div(entries, T);
+        k_csr_keys<<<g, T, 0, s>>>(edge_index, edge_type, range_list, E, entries, (int)n_nodes, (int)n_other,
+                                    (int)n_rel, by_src, drop_loops, k0, v0, v.counts);
+        if ((rc = sort_pairs_u32(k0, v0, k1, v1, entries, bits_for(sentinel), sort_ws, s))) return rc;
+        k_copy_u32_to_i32<<<g, T, 0, s>>>(v1, v.eid, entries);
+        k_csr_flags<<<g, T, 0, s>>>(edge_index, E, entries, by_src, sentinel, k1, v.eid, v.other, flags);
+        if ((rc = exclusive_scan_i32(flags, flags, entries, scan_ws, s))) return rc;
+        k_csr_segments<<<(unsigned)ceil_div(entries + 1, T), T, 0, s>>>(entries, sentinel, (int)n_rel, v.seg_cap, k1,
+                                                                        flags, v.seg_ptr, v.seg_node, v.seg_rel,
+                                                                        v.counts);
+    }
+    // relation-major listing of the segments
+    unsigned gs = (unsigned)ceil_div(v.seg_cap, T);
+    k_csr_pad<<<gs, T, 0, s>>>(v.seg_cap, (int)n_nodes, (int)n_rel, v.counts, v.seg_node, v.seg_rel, k0, v0);
+    k_group_ptr<int><<<(unsigned)ceil_div(v.seg_cap + 1, T), T, 0, s>>>(v.seg_node, v.seg_cap, (int)n_nodes,
+                                                                          v.node_ptr);
+    k_csr_degrees<<<(unsigned)ceil_div(n_nodes, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.seg_ptr, v.deg, v.inv_deg);
+    if ((rc = sort_pairs_u32(k0, v0, k1, v1, v.seg_cap, bits_for((uint64_t)n_rel), sort_ws, s))) return rc;
+    k_copy_u32_to_i32<<<gs, T, 0, s>>>(v1, v.rel_seg, v.seg_cap);
+    k_group_ptr<uint32_t><<<(unsigned)ceil_div(v.seg_cap + 1, T), T, 0, s>>>(k1, v.seg_cap, (int)n_rel, v.rel_seg_ptr);
+    TIPB_CHECK_LAUNCH("typed_csr_build");
+    return TIPB_OK;
+}
+
+}  // namespace tipb
+
+extern "C" {
+
+size_t tipb_typed_csr_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel) {
+    return (size_t)tipb::make_layout(n_entries, n_nodes, n_rel).total_bytes;
+}
+
+size_t tipb_typed_csr_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel) {
+    return tipb::csr_build_ws_bytes(n_entries, n_nodes, n_rel);
+}
+
+int tipb_typed_csr_layout(int64_t n_entries, int64_t n_nodes, int64_t n_rel, int64_t* offsets_bytes,
+                          int64_t* seg_capacity) {
+    tipb::CsrLayout L = tipb::make_layout(n_entries, n_nodes, n_rel);
+    for (int f = 0; f < TIPB_CSR_NFIELDS; ++f) offsets_bytes[f] = L.off[f];
+    if (seg_capacity) *seg_capacity = L.seg_cap;
+    return TIPB_OK;
+}
+
+int tipb_typed_csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list,
+                         int64_t n_edges, int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled,
+                         int drop_self_loops, void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(n_edges >= 0 && n_nodes > 0 && n_other > 0 && n_rel > 0, "typed_csr_build: bad sizes");
+    const int64_t entries = doubled ? 2 * n_edges : n_edges;
+    TIPB_CHECK_ARG(entries < (int64_t(1) << 31) - 2, "typed_csr_build: too many entries for int32 indexing");
+    TIPB_CHECK_ARG(n_nodes * n_rel < (int64_t(1) << 32) - 1, "typed_csr_build: n_nodes*n_rel must fit 32 bits");
+    TIPB_CHECK_ARG(n_edges == 0 || edge_index, "typed_csr_build: edge_index is NULL");
+    TIPB_CHECK_ARG(n_rel == 1 || edge_type || range_list, "typed_csr_build: need edge_type or range_list");
+    TIPB_CHECK_ARG(plan && plan_bytes >= tipb_typed_csr_bytes(entries, n_nodes, n_rel), "typed_csr_build: plan buffer too small");
+    TIPB_CHECK_ARG(ws && ws_bytes >= tipb_typed_csr_workspace_bytes(entries, n_nodes, n_rel), "typed_csr_build: workspace too small");
+    return tipb::csr_build(edge_index, edge_type, range_list, n_edges, n_nodes, n_other, n_rel, by_src, doubled,
+                           drop_self_loops, plan, ws, (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,398 @@
+"""Drop-in for the module API of the reference's src/layers.py, backed by libtipb200 (sm_100a).
+
+Same class names, constructor arguments, forward signatures, parameter names/shapes and
+initialisation draw order as the reference (so state_dicts and seeds carry over); the
+device work of every forward/backward goes through the C ABI in include/tipb200.h.
+There is no PyG, no torch_scatter, no Triton and no CPU path: CPU tensors are rejected.
+
+Reference lines (relative to the reference root) are cited per class.
+"""
+import math
+import pickle
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import Parameter as Param
+
+from . import neg_sampling as _ns
+from . import ops
+from ._lib import TipbError
+from .neg_sampling import typed_negative_sampling
+from .utils import *  # noqa: F401,F403  (the reference re-exports src.utils the same way)
+from .utils import is_sparse_identity, process_edges
+
+torch.manual_seed(1111)   # src/layers.py:13
+np.random.seed(1111)      # src/layers.py:14 (the device stream is seeded 1111 too, see neg_sampling._state)
+EPS = 1e-13               # src/layers.py:15
+
+
+def _require_cuda(t, who):
+    if not t.is_cuda:
+        raise TipbError(f"{who}: CUDA tensors only -- tip_b200 has no CPU fallback")
+
+
+# =============================================================================== convolutions
+class _RGCNBase(nn.Module):
+    """shared parameters/initialisation of MyRGCNConv and MyRGCNConv2 (src/layers.py:35-74, 115-155)"""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_bases, after_relu, bias=False, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases, self.after_relu = num_relations, num_bases, after_relu
+        self.basis = Param(torch.Tensor(num_bases, in_channels, out_channels))
+        self.att = Param(torch.Tensor(num_relations, num_bases))
+        self.root = Param(torch.Tensor(in_channels, out_channels))
+        if bias:
+            self.bias = Param(torch.Tensor(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # draw order att -> root -> basis is part of the seed contract
+        self.att.data.normal_(std=1 / np.sqrt(self.num_bases))
+        std = 2 / self.in_channels if self.after_relu else 1 / np.sqrt(self.in_channels)
+        self.root.data.normal_(std=std)
+        self.basis.data.normal_(std=std)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def _conv(self, x, edge_index, edge_type, range_list, relu=False):
+        _require_cuda(x, type(self).__name__)
+        assert edge_index.dtype == torch.long and edge_index.dim() == 2 and edge_index.size(0) == 2
+        n = x.size(0)
+        kw = dict(edge_type=edge_type, range_list=range_list)
+        plan_dst = ops.cached_plan(edge_index, n, self.num_relations, by_src=False, **kw)
+        plan_src = ops.cached_plan(edge_index, n, self.num_relations, by_src=True, **kw)
+        return ops.rgcn_conv(x, self.basis, self.att, self.root, plan_dst, plan_src, bias=self.bias, relu=relu)
+
+    def __repr__(self):
+        return "{}({}, {}, num_relations={})".format(type(self).__name__, self.in_channels, self.out_channels,
+                                                     self.num_relations)
+
+
+class MyRGCNConv(_RGCNBase):
+    """src/layers.py:21-99 -- edge_type in any order (the typed CSR is built by a stable GPU sort)."""
+
+    def forward(self, x, edge_index, edge_type):
+        return self._conv(x, edge_index, edge_type, None)
+
+
+class MyRGCNConv2(_RGCNBase):
+    """src/layers.py:102-193 -- edges sorted by relation with range_list[r] = (start, end).
+    Like the reference, `edge_type` is accepted and not read."""
+
+    def forward(self, x, edge_index, edge_type, range_list, _fused_relu=False):
+        return self._conv(x, edge_index, None, range_list.to(torch.long), relu=_fused_relu)
+
+
+class MyHierarchyConv(nn.Module):
+    """directed mean-aggregation protein -> drug (src/layers.py:196-247)"""
+
+    def __init__(self, in_dim, out_dim, unigue_source_num, unique_target_num, is_after_relu=True, is_bias=False,
+                 **kwargs):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.unique_source_num, self.unique_target_num = unigue_source_num, unique_target_num
+        self.is_after_relu = is_after_relu
+        self.weight = Param(torch.Tensor(in_dim, out_dim))
+        if is_bias:
+            self.bias = Param(torch.Tensor(out_dim))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        std = 1 / np.sqrt(self.in_dim) if self.is_after_relu else 2 / np.sqrt(self.in_dim)
+        self.weight.data.normal_(std=std)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, x, edge_index, range_list):
+        _require_cuda(x, "MyHierarchyConv")
+        if self.bias is not None:
+            # the reference's `if self.bias:` raises for a multi-element tensor; same outcome here
+            raise RuntimeError("Boolean value of Tensor with more than one value is ambiguous")
+        n = self.unique_source_num + self.unique_target_num
+        assert x.size(0) == n, "x must hold unique_source_num + unique_target_num rows"
+        plan_dst = ops.cached_plan(edge_index, n, 1, by_src=False)
+        plan_src = ops.cached_plan(edge_index, n, 1, by_src=True)
+        out = ops.hier_conv(x, self.weight, plan_dst, plan_src, self.unique_source_num, self.unique_target_num)
+        assert out.shape[0] == self.unique_target_num
+        return out
+
+    def __repr__(self):
+        return "{}({}, {}".format(type(self).__name__, self.in_dim, self.out_dim)
+
+
+class _Lin(nn.Module):
+    """holds `weight` [out, in] under the name torch_geometric's GCNConv uses (`lin.weight`)"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = Param(torch.Tensor(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = math.sqrt(6.0 / (self.weight.size(0) + self.weight.size(1)))   # glorot
+        self.weight.data.uniform_(-bound, bound)
+
+
+class GCNConv(nn.Module):
+    """torch_geometric 2.0.1 GCNConv(in, out, cached=True) as used by PPEncoder (src/layers.py:386-387):
+    parameter names `lin.weight`, `bias`; symmetric normalisation with remaining self loops; the
+    normalised graph of the FIRST call is cached (here: the typed CSR + deg^-1/2)."""
+
+    def __init__(self, in_channels, out_channels, cached=False, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels, self.cached = in_channels, out_channels, cached
+        self.lin = _Lin(in_channels, out_channels)       # PyG's Linear initialises itself in __init__ ...
+        self.bias = Param(torch.Tensor(out_channels))
+        self._cache = None
+        self._identity_ok = {}
+        self.reset_parameters()                          # ... and GCNConv.reset_parameters draws it again
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        self.bias.data.zero_()
+        self._cache = None
+
+    def _graph(self, edge_index, n):
+        if self._cache is not None:
+            return self._cache
+        plan_dst = ops.cached_plan(edge_index, n, 1, by_src=False, drop_self_loops=True)
+        plan_src = ops.cached_plan(edge_index, n, 1, by_src=True, drop_self_loops=True)
+        graph = (plan_dst, plan_src, ops.gcn_norm(plan_dst))
+        if self.cached:
+            self._cache = graph
+        return graph
+
+    def _linear(self, x):
+        if x.is_sparse:
+            key = (x._indices().data_ptr(), tuple(x.shape))
+            if key not in self._identity_ok:
+                self._identity_ok[key] = is_sparse_identity(x)     # one-time check (host sync at setup)
+            if self._identity_ok[key]:
+                return self.lin.weight.t().contiguous()            # I @ W^T
+            return torch.sparse.mm(x, self.lin.weight.t())         # general sparse features (not on the TIP path)
+        return x @ self.lin.weight.t()
+
+    def forward(self, x, edge_index, _fused_relu=False):
+        assert edge_index.dtype == torch.long and edge_index.dim() == 2 and edge_index.size(0) == 2
+        if not edge_index.is_cuda:
+            raise TipbError("GCNConv: CUDA tensors only -- tip_b200 has no CPU fallback")
+        plan_dst, plan_src, dis = self._graph(edge_index, x.size(0))
+        return ops.gcn_spmm(self._linear(x), self.bias, plan_dst, plan_src, dis, relu=_fused_relu)
+
+
+# =============================================================================== encoders
+class PPEncoder(nn.Module):
+    """2 x GCNConv + ReLU on the protein-protein graph (src/layers.py:380-395)"""
+
+    def __init__(self, in_dim, hid1=32, hid2=16):
+        super().__init__()
+        self.out_dim = hid2
+        self.conv1 = GCNConv(in_dim, hid1, cached=True)
+        self.conv2 = GCNConv(hid1, hid2, cached=True)
+
+    def forward(self, x, edge_index):
+        x = self.conv1(x, edge_index, _fused_relu=True)      # bias + ReLU fused into the SpMM epilogue
+        return self.conv2(x, edge_index)
+
+
+class FMEncoder(nn.Module):
+    """P-P GCN -> P->D hierarchy -> drug embedding (cat | add) -> 2 x R-GCN (src/layers.py:471-553)"""
+
+    def __init__(self, device, in_dim_drug, num_dd_et, in_dim_prot, uni_num_prot, uni_num_drug, prot_drug_dim=64,
+                 num_base=32, n_embed=64, n_hid1=32, n_hid2=16, mod="cat"):
+        super().__init__()
+        self.num_et, self.out_dim = num_dd_et, n_hid2
+        self.uni_num_drug, self.uni_num_prot = uni_num_drug, uni_num_prot
+        self.mod = mod
+        assert mod in {"add", "cat"}
+        if mod == "add":
+            assert n_embed == prot_drug_dim
+        self.pp_encoder = PPEncoder(in_dim_prot)
+        self.embed = Param(torch.Tensor(in_dim_drug, n_embed))
+        self.hgcn = MyHierarchyConv(self.pp_encoder.out_dim, prot_drug_dim, uni_num_prot, uni_num_drug)
+        self.hdrug = torch.zeros((self.uni_num_drug, self.pp_encoder.out_dim)).to(device)
+        rgcn_in_dim = n_embed + self.hgcn.out_dim if mod == "cat" else n_embed
+        self.rgcn1 = MyRGCNConv2(rgcn_in_dim, n_hid1, num_dd_et, num_base, after_relu=False)
+        self.rgcn2 = MyRGCNConv2(n_hid1, n_hid2, num_dd_et, num_base, after_relu=True)
+        self._identity_ok = {}
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embed.data.normal_()
+
+    def _embed(self, x_drug):
+        if x_drug.is_sparse:
+            key = (x_drug._indices().data_ptr(), tuple(x_drug.shape))
+            if key not in self._identity_ok:
+                self._identity_ok[key] = is_sparse_identity(x_drug)
+            if self._identity_ok[key]:
+                return self.embed                                   # I @ embed
+            return torch.sparse.mm(x_drug, self.embed)
+        return torch.matmul(x_drug, self.embed)
+
+    def forward(self, x_drug, dd_edge_index, dd_edge_type, dd_range_list, d_norm, x_prot, pp_edge_index,
+                dp_edge_index, dp_range_list):
+        x_prot = self.pp_encoder(x_prot, pp_edge_index)
+        x_prot = torch.cat((x_prot, self.hdrug.to(x_prot.device)))
+        x_prot = self.hgcn(x_prot, dp_edge_index, dp_range_list)
+        x_drug = self._embed(x_drug) / d_norm.view(-1, 1)
+        x_drug = torch.cat((x_drug, x_prot), dim=1) if self.mod == "cat" else x_drug + x_prot
+        x_drug = self.rgcn1(x_drug, dd_edge_index, dd_edge_type, dd_range_list, _fused_relu=True)
+        return self.rgcn2(x_drug, dd_edge_index, dd_edge_type, dd_range_list)
+
+
+class FMEncoderCat(FMEncoder):
+    """the stale 'cat'-only duplicate of FMEncoder (src/layers.py:401-468)"""
+
+    def __init__(self, device, in_dim_drug, num_dd_et, in_dim_prot, uni_num_prot, uni_num_drug, prot_drug_dim=16,
+                 num_base=32, n_embed=48, n_hid1=32, n_hid2=16):
+        super().__init__(device, in_dim_drug, num_dd_et, in_dim_prot, uni_num_prot, uni_num_drug, prot_drug_dim,
+                         num_base, n_embed, n_hid1, n_hid2, mod="cat")
+
+
+# =============================================================================== decoder
+class MultiInnerProductDecoder(nn.Module):
+    """DistMult scorer z_i^T diag(w_r) z_j (src/layers.py:581-595)"""
+
+    def __init__(self, in_dim, num_et):
+        super().__init__()
+        self.num_et, self.in_dim = num_et, in_dim
+        self.weight = Param(torch.Tensor(num_et, in_dim))
+        self.reset_parameters()
+
+    def forward(self, z, edge_index, edge_type, sigmoid=True):
+        _require_cuda(z, "MultiInnerProductDecoder")
+        return ops.decoder_score(z, self.weight, edge_index, edge_type, sigmoid)
+
+    def sweep(self, z, sigmoid=True):
+        """scores of all num_nodes^2 pairs for every relation: [num_et, N, N] (BASELINE.json config 5)"""
+        return ops.decoder_sweep(z, self.weight, sigmoid)
+
+    def reset_parameters(self):
+        self.weight.data.normal_(std=1 / np.sqrt(self.in_dim))
+
+
+# =============================================================================== training wrapper
+class MyGAE(nn.Module):
+    """src/layers.py:253-258 (the TIP path always passes a decoder)"""
+
+    def __init__(self, encoder, decoder=None):
+        super().__init__()
+        self.encoder = encoder
+        if decoder is None:
+            raise TipbError("MyGAE without a decoder needs torch_geometric's InnerProductDecoder (not on the TIP path)")
+        self.decoder = decoder
+
+
+class Setting(object):
+    """src/layers.py:260-269"""
+
+    def __init__(self, sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32):
+        self.sp_rate, self.lr = sp_rate, lr
+        self.prot_drug_dim, self.n_embed, self.n_hid1, self.n_hid2, self.num_base = (prot_drug_dim, n_embed, n_hid1,
+                                                                                     n_hid2, num_base)
+
+
+class _Data(object):
+    """attribute bag standing in for torch_geometric.data.Data.from_dict(...).to(device)"""
+
+    def __init__(self, d, device):
+        for k, v in d.items():
+            setattr(self, k, v.to(device) if torch.is_tensor(v) else v)
+
+
+class TIP(nn.Module):
+    """src/layers.py:272-375.  `data_path` is the reference's data_dict.pkl (prepare.py:13-47);
+    a ready dict can be passed instead through `data=`."""
+
+    def __init__(self, settings, device, mod="cat", data_path="./data/data_dict.pkl", data=None):
+        super().__init__()
+        self.mod = mod
+        assert mod in {"cat", "add"}
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise TipbError("TIP: CUDA device required -- tip_b200 has no CPU fallback")
+        self.settings = settings
+        self.data = self._prepare_data(data_path, settings.sp_rate, data)
+        self._prepare_model()
+        self._neg_plan = None
+        self._neg_index = None
+
+    def _prepare_data(self, data_path, sp_rate, data_dict):
+        if data_dict is None:
+            with open(data_path, "rb") as f:
+                data_dict = pickle.load(f)
+        data_dict = dict(data_dict)
+        if sp_rate != 0.9:
+            # same single numpy-compatible stream as the reference: hand it to numpy for the split, take it back
+            np.random.set_state(_ns.get_state(self.device))
+            (data_dict["dd_train_idx"], data_dict["dd_train_et"], data_dict["dd_train_range"],
+             data_dict["dd_test_idx"], data_dict["dd_test_et"], data_dict["dd_test_range"]) = \
+                process_edges(data_dict["dd_edge_index"], p=sp_rate)
+            _ns.set_state(np.random.get_state(), self.device)
+        data = _Data(data_dict, self.device)
+        data.dd_train_range = data.dd_train_range.to(torch.long)
+        data.dd_test_range = data.dd_test_range.to(torch.long)
+        self.test_neg_index = typed_negative_sampling(data.dd_test_idx, data.n_drug, data.dd_test_range)
+        return data
+
+    def _prepare_model(self):
+        d, s = self.data, self.settings
+        self.encoder = FMEncoder(self.device, d.n_drug_feat, d.n_dd_et, d.n_prot, d.n_prot, d.n_drug, s.prot_drug_dim,
+                                 s.num_base, s.n_embed, s.n_hid1, s.n_hid2, mod=self.mod).to(self.device)
+        with torch.no_grad():   # the reference's warm-up encoder call (src/layers.py:319); builds and caches the plans
+            self.embeddings = self._encode()
+        self.decoder = MultiInnerProductDecoder(s.n_hid2, d.n_dd_et).to(self.device)
+        self._pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range,
+                                         by_src=False, doubled=True)
+
+    def _encode(self):
+        d = self.data
+        return self.encoder(d.d_feat, d.dd_train_idx, d.dd_train_et, d.dd_train_range, d.d_norm, d.p_feat,
+                            d.pp_train_indices, d.dp_edge_index, d.dp_range_list)
+
+    def forward(self, check_status=True):
+        d = self.data
+        self.embeddings = self._encode()
+        if self._neg_index is None:
+            self._neg_index = torch.empty_like(d.dd_train_idx)
+            self._neg_plan = ops.TypedCSR(d.dd_train_idx.shape[1], d.n_drug, d.n_dd_et, self.device, by_src=False,
+                                          doubled=True)
+        neg_index = typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range, check_status=check_status,
+                                            out=self._neg_index)
+        self._neg_plan.build(neg_index, range_list=d.dd_train_range)
+        # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient
+        return ops.bce_loss(self.embeddings, self.decoder.weight, self._pos_plan, self._neg_plan)
+
+    def pred(self, dd_idx, dd_et):
+        return self.decoder(self.embeddings, dd_idx, dd_et)
+
+    def test(self, print_output=True):
+        self.eval()
+        d = self.data
+        with torch.no_grad():
+            pos_score = self.decoder(self.embeddings, d.dd_test_idx, d.dd_test_et)
+            neg_score = self.decoder(self.embeddings, self.test_neg_index, d.dd_test_et)
+        return self.compute_auprc_auroc_ap_by_et(pos_score, neg_score, d.dd_test_range, print_output)
+
+    def compute_auprc_auroc_ap_by_et(self, pos_score, neg_score, dd_range, print_out):
+        from .utils import auprc_auroc_ap
+        record = np.zeros((3, self.data.n_dd_et))
+        pos_score, neg_score, dd_range = pos_score.cpu(), neg_score.cpu(), dd_range.cpu()
+        for i in range(dd_range.shape[0]):
+            start, end = int(dd_range[i][0]), int(dd_range[i][1])
+            p_s, n_s = pos_score[start:end], neg_score[start:end]
+            score = torch.cat([p_s, n_s])
+            target = torch.cat([torch.ones(p_s.shape[0]), torch.zeros(n_s.shape[0])])
+            record[0, i], record[1, i], record[2, i] = auprc_auroc_ap(target, score)
+        if print_out:
+            auprc, auroc, ap = record.sum(axis=1) / self.data.n_dd_et
+            print("On test set: auprc:{:0.4f}   auroc:{:0.4f}   ap@50:{:0.4f}    ".format(auprc, auroc, ap))
+        return record

@@ -1,0 +1,360 @@
+"""torch.autograd.Function wrappers over the C ABI (libtipb200.so).
+
+Everything here is plumbing: tensors are made contiguous, outputs and scratch
+are allocated with torch, raw pointers + the current CUDA stream go to the
+library.  No computation of the hot path happens in Python, and nothing falls
+back to torch ops when the library is missing (tip_b200._lib raises).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+
+# ----------------------------------------------------------------------------- scratch memory
+_workspaces = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """A reusable scratch buffer (grown geometrically).  All library calls are ordered on the
+    current stream, so one buffer per (device, tag) is enough."""
+    key = (device.index, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise _lib.TipbError(f"tip_b200 computes in fp32; got {t.dtype}")
+    return t.contiguous()
+
+
+def _i64c(t):
+    if t.dtype != torch.long:
+        raise AssertionError("edge tensors must be torch.long (as torch_geometric asserts)")
+    return t.contiguous()
+
+
+def _next_pow2(v, lo=4):
+    p = lo
+    while p < v:
+        p *= 2
+    return p
+
+
+# ----------------------------------------------------------------------------- typed CSR plans
+class TypedCSR(object):
+    """Device-side index structure built by tipb_typed_csr_build (tip_b200/csrc/typed_csr.cu)."""
+
+    def __init__(self, n_edges, n_nodes, n_rel, device, by_src=False, doubled=False, drop_self_loops=False,
+                 n_other=None):
+        self.n_edges, self.n_nodes, self.n_rel = int(n_edges), int(n_nodes), int(n_rel)
+        self.n_other = int(n_other if n_other is not None else n_nodes)
+        self.by_src, self.doubled, self.drop_self_loops = bool(by_src), bool(doubled), bool(drop_self_loops)
+        self.n_entries = self.n_edges * (2 if doubled else 1)
+        self.device = device
+        L = lib()
+        self.nbytes = L.tipb_typed_csr_bytes(self.n_entries, self.n_nodes, self.n_rel)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self._layout, self.seg_cap = _lib.csr_layout(self.n_entries, self.n_nodes, self.n_rel)
+        self._ws_bytes = L.tipb_typed_csr_workspace_bytes(self.n_entries, self.n_nodes, self.n_rel)
+
+    def build(self, edge_index, edge_type=None, range_list=None):
+        edge_index = _i64c(edge_index)
+        assert edge_index.dim() == 2 and edge_index.shape[0] == 2 and edge_index.shape[1] == self.n_edges
+        edge_type = None if edge_type is None else _i64c(edge_type)
+        range_list = None if range_list is None else _i64c(range_list.to(torch.long))
+        ws = workspace(self._ws_bytes, self.device, "csr")
+        check(lib().tipb_typed_csr_build(ptr(edge_index), ptr(edge_type), ptr(range_list), self.n_edges, self.n_nodes,
+                                         self.n_other, self.n_rel, int(self.by_src), int(self.doubled),
+                                         int(self.drop_self_loops), ptr(self.buf), self.nbytes, ptr(ws), ws.numel(),
+                                         stream()), "typed_csr_build")
+        return self
+
+    # ---- views (tests, inv_deg for the backward pass)
+    def field(self, name):
+        sizes = {"counts": 16, "eid": self.n_entries, "other": self.n_entries, "seg_ptr": self.seg_cap + 1,
+                 "seg_node": self.seg_cap, "seg_rel": self.seg_cap, "node_ptr": self.n_nodes + 1, "deg": self.n_nodes,
+                 "inv_deg": self.n_nodes, "rel_seg_ptr": self.n_rel + 1, "rel_seg": self.seg_cap}
+        off, n = self._layout[name], sizes[name]
+        raw = self.buf[off:off + 4 * n]
+        return raw.view(torch.float32 if name == "inv_deg" else torch.int32)
+
+    @property
+    def inv_deg(self):
+        return self.field("inv_deg")
+
+    def check_status(self):
+        """One host sync: raises if an index was out of range when the plan was built."""
+        if int(self.field("counts")[2]) != 0:
+            raise IndexError("edge_index / edge_type contains an out-of-range index")
+        return self
+
+
+_plan_cache = {}
+
+
+def _tensor_key(t):
+    return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+
+
+def cached_plan(edge_index, n_nodes, n_rel=1, edge_type=None, range_list=None, validate=True, **flags):
+    """Plans are cached per (edge tensors identity/version, flags): the reference's modules are
+    stateless but PyG's GCNConv(cached=True) keeps its normalised graph the same way."""
+    key = (_tensor_key(edge_index), _tensor_key(edge_type), _tensor_key(range_list), int(n_nodes), int(n_rel),
+           tuple(sorted(flags.items())))
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) > 64:
+            _plan_cache.clear()
+        plan = TypedCSR(edge_index.shape[1], n_nodes, n_rel, edge_index.device, **flags)
+        plan.build(edge_index, edge_type, range_list)
+        if validate:
+            plan.check_status()
+        # keep the key tensors alive so that data_ptr() cannot be recycled under the cache
+        plan._keepalive = (edge_index, edge_type, range_list)
+        _plan_cache[key] = plan
+    return plan
+
+
+# ----------------------------------------------------------------------------- R-GCN
+class _RGCNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, basis, att, root, plan_dst, plan_src, relu):
+        x, basis, att, root = _f32c(x), _f32c(basis), _f32c(att), _f32c(root)
+        n, f_in = x.shape
+        n_bases, _, f_out = basis.shape
+        n_rel = att.shape[0]
+        assert n == plan_dst.n_nodes and n_rel == plan_dst.n_rel
+        L = lib()
+        out = torch.empty((n, f_out), dtype=torch.float32, device=x.device)
+        g_saved = torch.empty((n, n_bases, f_in), dtype=torch.float32, device=x.device)
+        ws_bytes = L.tipb_rgcn_workspace_bytes(plan_dst.n_entries, n, n_rel, f_in, f_out, n_bases)
+        ws = workspace(ws_bytes, x.device)
+        check(L.tipb_rgcn_fwd(ptr(plan_dst.buf), plan_dst.n_entries, n, n_rel, ptr(x), ptr(basis), ptr(att), ptr(root),
+                              None, f_in, f_out, n_bases, int(relu), ptr(out), ptr(g_saved), ptr(ws), ws.numel(),
+                              stream()), "rgcn_fwd")
+        ctx.save_for_backward(x, basis, att, root, g_saved, out)
+        ctx.plan_dst, ctx.plan_src, ctx.relu = plan_dst, plan_src, relu
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, basis, att, root, g_saved, out = ctx.saved_tensors
+        plan_dst, plan_src = ctx.plan_dst, ctx.plan_src
+        grad_out = _f32c(grad_out)
+        n, f_in = x.shape
+        n_bases, _, f_out = basis.shape
+        n_rel = att.shape[0]
+        L = lib()
+        d_x, d_basis, d_att, d_root = (torch.empty_like(t) for t in (x, basis, att, root))
+        ws_bytes = L.tipb_rgcn_workspace_bytes(plan_src.n_entries, n, n_rel, f_in, f_out, n_bases)
+        ws = workspace(ws_bytes, x.device)
+        check(L.tipb_rgcn_bwd(ptr(plan_src.buf), plan_src.n_entries, n, n_rel, ptr(plan_dst.inv_deg), ptr(x), ptr(basis),
+                              ptr(att), ptr(root), ptr(g_saved), ptr(grad_out), ptr(out) if ctx.relu else None,
+                              f_in, f_out, n_bases, ptr(d_x), ptr(d_basis), ptr(d_att), ptr(d_root), None, ptr(ws),
+                              ws.numel(), stream()), "rgcn_bwd")
+        return d_x, d_basis, d_att, d_root, None, None, None
+
+
+def rgcn_conv(x, basis, att, root, plan_dst, plan_src, bias=None, relu=False):
+    """out = mean-aggregated basis-decomposed relational conv + x @ root (+ bias) (+ ReLU).
+    Feature widths that are not powers of two in [4,128] are zero-padded here (exact)."""
+    n_bases, f_in, f_out = basis.shape
+    fi, fo = _next_pow2(f_in), _next_pow2(f_out)
+    if fi > 128 or fo > 128:
+        raise _lib.TipbError("rgcn_conv supports feature widths up to 128")
+    if (fi, fo) != (f_in, f_out):
+        x = F.pad(x, (0, fi - f_in))
+        basis = F.pad(basis, (0, fo - f_out, 0, fi - f_in))
+        root = F.pad(root, (0, fo - f_out, 0, fi - f_in))
+    fuse_relu = relu and bias is None
+    out = _RGCNFunction.apply(x, basis, att, root, plan_dst, plan_src, fuse_relu)
+    if fo != f_out:
+        out = out[:, :f_out]
+    if bias is not None:
+        out = out + bias
+        if relu:
+            out = torch.relu(out)
+    return out
+
+
+# ----------------------------------------------------------------------------- GCN SpMM
+class _GCNSpmmFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, plan_dst, plan_src, dis, relu):
+        x = _f32c(x)
+        n, f = x.shape
+        out = torch.empty_like(x)
+        check(lib().tipb_gcn_spmm(ptr(plan_dst.buf), plan_dst.n_entries, n, ptr(dis), ptr(dis), ptr(x),
+                                  None if bias is None else ptr(_f32c(bias)), f, int(relu), ptr(out), stream()),
+              "gcn_spmm")
+        ctx.plan_src, ctx.dis, ctx.relu, ctx.has_bias = plan_src, dis, relu, bias is not None
+        if relu:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad_out = _f32c(grad_out)
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            grad_out = grad_out * (out > 0)
+        n, f = grad_out.shape
+        d_x = torch.empty_like(grad_out)
+        plan = ctx.plan_src
+        check(lib().tipb_gcn_spmm(ptr(plan.buf), plan.n_entries, n, ptr(ctx.dis), ptr(ctx.dis), ptr(grad_out), None, f, 0,
+                                  ptr(d_x), stream()), "gcn_spmm(bwd)")
+        d_bias = grad_out.sum(dim=0) if ctx.has_bias else None
+        return d_x, d_bias, None, None, None, None
+
+
+def gcn_norm(plan_dst):
+    dis = torch.empty(plan_dst.n_nodes, dtype=torch.float32, device=plan_dst.device)
+    check(lib().tipb_gcn_norm(ptr(plan_dst.buf), plan_dst.n_entries, plan_dst.n_nodes, ptr(dis), stream()), "gcn_norm")
+    return dis
+
+
+def gcn_spmm(x, bias, plan_dst, plan_src, dis, relu=False):
+    f = x.shape[1]
+    fp = _next_pow2(f)
+    if fp > 128:
+        raise _lib.TipbError("gcn_spmm supports feature widths up to 128")
+    if fp != f:
+        x = F.pad(x, (0, fp - f))
+        bias = None if bias is None else F.pad(bias, (0, fp - f))
+    out = _GCNSpmmFunction.apply(x, bias, plan_dst, plan_src, dis, relu)
+    return out if fp == f else out[:, :f]
+
+
+# ----------------------------------------------------------------------------- hierarchy conv
+class _HierFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, plan_dst, plan_src, n_source, n_target):
+        x, weight = _f32c(x), _f32c(weight)
+        f_in, f_out = weight.shape
+        mean = torch.empty((n_target, f_in), dtype=torch.float32, device=x.device)
+        out = torch.empty((n_target, f_out), dtype=torch.float32, device=x.device)
+        check(lib().tipb_hier_fwd(ptr(plan_dst.buf), plan_dst.n_entries, n_source, n_target, ptr(x), ptr(weight), f_in,
+                                  f_out, ptr(mean), ptr(out), stream()), "hier_fwd")
+        ctx.save_for_backward(mean, weight)
+        ctx.plan_dst, ctx.plan_src, ctx.n_source, ctx.n_target = plan_dst, plan_src, n_source, n_target
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mean, weight = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        f_in, f_out = weight.shape
+        n_source, n_target = ctx.n_source, ctx.n_target
+        L = lib()
+        d_x = torch.empty((n_source + n_target, f_in), dtype=torch.float32, device=grad_out.device)
+        d_w = torch.empty_like(weight)
+        ws = workspace(L.tipb_hier_workspace_bytes(n_source, n_target, f_in, f_out), grad_out.device)
+        check(L.tipb_hier_bwd(ptr(ctx.plan_src.buf), ctx.plan_src.n_entries, n_source, n_target, ptr(ctx.plan_dst.inv_deg),
+                              ptr(mean), ptr(weight), ptr(grad_out), f_in, f_out, ptr(d_x), ptr(d_w), ptr(ws), ws.numel(),
+                              stream()), "hier_bwd")
+        return d_x, d_w, None, None, None, None
+
+
+def hier_conv(x, weight, plan_dst, plan_src, n_source, n_target):
+    f_in, f_out = weight.shape
+    fi, fo = _next_pow2(f_in), _next_pow2(f_out)
+    if (fi, fo) != (f_in, f_out):
+        x = F.pad(x, (0, fi - f_in))
+        weight = F.pad(weight, (0, fo - f_out, 0, fi - f_in))
+    out = _HierFunction.apply(x, weight, plan_dst, plan_src, n_source, n_target)
+    return out if fo == f_out else out[:, :f_out]
+
+
+# ----------------------------------------------------------------------------- decoder
+class _DecoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, edge_index, edge_type, sigmoid):
+        z, weight = _f32c(z), _f32c(weight)
+        edge_index, edge_type = _i64c(edge_index), _i64c(edge_type)
+        n_edges = edge_index.shape[1]
+        out = torch.empty(n_edges, dtype=torch.float32, device=z.device)
+        check(lib().tipb_decoder_fwd(ptr(z), ptr(weight), ptr(edge_index), ptr(edge_type), n_edges, z.shape[0],
+                                     weight.shape[0], z.shape[1], int(sigmoid), ptr(out), stream()), "decoder_fwd")
+        ctx.save_for_backward(z, weight, edge_index, edge_type)
+        ctx.sigmoid = sigmoid
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z, weight, edge_index, edge_type = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        n_edges, n_nodes, n_rel, dim = edge_index.shape[1], z.shape[0], weight.shape[0], z.shape[1]
+        plan = cached_plan(edge_index, n_nodes, n_rel, edge_type=edge_type, validate=False, by_src=False, doubled=True)
+        L = lib()
+        d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
+        ws = workspace(L.tipb_decoder_workspace_bytes(n_edges, n_nodes, n_rel, dim), z.device)
+        check(L.tipb_decoder_bwd(ptr(plan.buf), n_edges, n_nodes, n_rel, ptr(z), ptr(weight), ptr(grad_out), dim,
+                                 int(ctx.sigmoid), ptr(d_z), ptr(d_w), ptr(ws), ws.numel(), stream()), "decoder_bwd")
+        return d_z, d_w, None, None, None
+
+
+def decoder_score(z, weight, edge_index, edge_type, sigmoid=True):
+    dim = z.shape[1]
+    dp = _next_pow2(dim)
+    if dp > 32:
+        raise _lib.TipbError("decoder supports embedding widths up to 32")
+    if dp != dim:
+        z, weight = F.pad(z, (0, dp - dim)), F.pad(weight, (0, dp - dim))
+    return _DecoderFunction.apply(z, weight, edge_index, edge_type, sigmoid)
+
+
+class _BCELossFunction(torch.autograd.Function):
+    """loss = -mean(log(sig(pos)+eps)) - mean(log(1-sig(neg)+eps)); gradient computed in the forward pass."""
+
+    @staticmethod
+    def forward(ctx, z, weight, plan_pos, plan_neg):
+        z, weight = _f32c(z), _f32c(weight)
+        n_nodes, dim = z.shape
+        n_rel = weight.shape[0]
+        L = lib()
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+        d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
+        need = max(L.tipb_decoder_workspace_bytes(plan_pos.n_edges, n_nodes, n_rel, dim),
+                   L.tipb_decoder_workspace_bytes(plan_neg.n_edges, n_nodes, n_rel, dim))
+        ws = workspace(need, z.device)
+        for plan, sign, acc in ((plan_pos, 1, 0), (plan_neg, -1, 1)):
+            check(L.tipb_decoder_bce_fused(ptr(plan.buf), plan.n_edges, n_nodes, n_rel, ptr(z), ptr(weight), dim, sign, acc,
+                                           ptr(loss), ptr(d_z), ptr(d_w), ptr(ws), ws.numel(), stream()),
+                  "decoder_bce_fused")
+        ctx.save_for_backward(d_z, d_w)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        d_z, d_w = ctx.saved_tensors
+        return d_z * grad_loss, d_w * grad_loss, None, None
+
+
+def bce_loss(z, weight, plan_pos, plan_neg):
+    dim = z.shape[1]
+    dp = _next_pow2(dim)
+    if dp > 32:
+        raise _lib.TipbError("decoder supports embedding widths up to 32")
+    if dp != dim:
+        z, weight = F.pad(z, (0, dp - dim)), F.pad(weight, (0, dp - dim))
+    return _BCELossFunction.apply(z, weight, plan_pos, plan_neg)
+
+
+def decoder_sweep(z, weight, sigmoid=True):
+    z, weight = _f32c(z), _f32c(weight)
+    n, dim = z.shape
+    out = torch.empty((weight.shape[0], n, n), dtype=torch.float32, device=z.device)
+    check(lib().tipb_decoder_sweep(ptr(z), ptr(weight), n, weight.shape[0], dim, int(sigmoid), ptr(out), stream()),
+          "decoder_sweep")
+    return out
+
+
+__all__ = ["TypedCSR", "cached_plan", "rgcn_conv", "gcn_norm", "gcn_spmm", "hier_conv", "decoder_score", "bce_loss",
+           "decoder_sweep", "workspace", "math"]
