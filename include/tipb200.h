@@ -90,6 +90,10 @@ int tipb_typed_csr_build(const int64_t* edge_index /* [2,n_edges] */, const int6
  * Evaluated as  H[s] = sum_{e in segment s} x_j   (segmented gather-reduce over the typed CSR),
  *               G[i,b,:] = sum_{s in node i} att[rel_s,b] H[s]  and  out_i = inv_deg_i G[i] . basis + x_i root.
  * `g_saved` ([n_nodes, n_bases, f_in], written by fwd) is what bwd needs for d_basis. */
+/* the edge pass on its own: out[s,:] = sum_{e in segment s} feat[other_e,:]  (out: [seg_capacity, f]); this is the
+ * kernel the roofline in bench.py is quoted on */
+int tipb_seg_aggregate(const void* plan, int64_t n_entries, int64_t n_nodes, int64_t n_rel, const float* feat,
+                       int64_t n_feat_rows, int f, float* out, void* stream);
 size_t tipb_rgcn_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel, int f_in, int f_out, int n_bases);
 int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, int64_t n_rel, const float* x,
                   const float* basis, const float* att, const float* root, const float* bias /* or NULL */,
@@ -157,7 +161,7 @@ int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_li
                           int64_t n_nodes, int64_t n_rel, uint32_t* member, void* stream);
 /* budget_words = how many fresh MT19937 words to generate for this call (an upper bound on what the
  * rejection loops will consume; *status gets bit0 if it was too small, bit1 if a relation needed more
- * than 64 retry rounds -- the caller then restores the state, enlarges the budget and calls again). */
+ * than ~n_rel*8+65536 retry rounds in total -- the caller then restores the state, enlarges the budget and calls again). */
 size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t budget_words);
 int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* member, const int64_t* range_list,
                     int64_t n_edges, int64_t n_nodes, int64_t n_rel, int64_t budget_words,

@@ -29,7 +29,6 @@ namespace tipb {
 
 constexpr int MT_N = 624, MT_M = 397, MT_LAG = MT_N - MT_M;  // 227
 constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MATRIX_A = 0x9908b0dfu;
-constexpr int MAX_ROUNDS = 64;
 constexpr int RING = 2048;
 
 enum { NEG_STATUS_OUT_OF_WORDS = 1, NEG_STATUS_TOO_MANY_ROUNDS = 2 };
@@ -113,30 +112,35 @@ __device__ __forceinline__ bool is_member(const uint32_t* __restrict__ bits, int
     return (bits[key >> 5] >> (key & 31)) & 1u;
 }
 
-// rounds[r][q] = (start, len) in the accepted stream; n_rounds[r]; chain_out[0] = accepted values consumed
+// rounds[round_ptr[r] + q] = (start, len) in the accepted stream, q < n_rounds[r] (one flat table for all
+// relations, `round_cap` entries); chain_out[0] = accepted values consumed
 __global__ void __launch_bounds__(1024)
 k_chain(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
-        int64_t words_per_rel, const int64_t* __restrict__ range_list, int n_rel, int* __restrict__ rounds,
-        int* __restrict__ n_rounds, int* __restrict__ chain_out, int* __restrict__ status) {
+        int64_t words_per_rel, const int64_t* __restrict__ range_list, int n_rel, int round_cap,
+        int* __restrict__ rounds, int* __restrict__ round_ptr, int* __restrict__ n_rounds, int* __restrict__ chain_out,
+        int* __restrict__ status) {
     __shared__ int sw[32];
     __shared__ int s_total;
     const int n_acc = *n_accepted_ptr;
     int base = 0;
+    int used = 0;  // entries of the flat round table handed out so far
     for (int r = 0; r < n_rel; ++r) {
         const uint32_t* bits = member + int64_t(r) * words_per_rel;
         int n = int(range_list[2 * r + 1] - range_list[2 * r]);
         int q = 0;
+        if (threadIdx.x == 0) round_ptr[r] = used;
         while (n > 0) {
-            if (base + n > n_acc || q >= MAX_ROUNDS) {
+            if (base + n > n_acc || used >= round_cap) {
                 if (threadIdx.x == 0) atomicOr(status, base + n > n_acc ? NEG_STATUS_OUT_OF_WORDS : NEG_STATUS_TOO_MANY_ROUNDS);
                 n = 0;
                 base = n_acc;  // poison: every later relation fails the same way
                 break;
             }
             if (threadIdx.x == 0) {
-                rounds[(int64_t(r) * MAX_ROUNDS + q) * 2] = base;
-                rounds[(int64_t(r) * MAX_ROUNDS + q) * 2 + 1] = n;
+                rounds[2 * used] = base;
+                rounds[2 * used + 1] = n;
             }
+            ++used;
             int c = 0;
             for (int i = threadIdx.x; i < n; i += 1024) c += is_member(bits, A[base + i]) ? 1 : 0;
             c = warp_sum_i(c);
@@ -161,8 +165,9 @@ k_chain(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const
 // one CTA per relation: replay the rounds, write int64 pairs
 __global__ void __launch_bounds__(256)
 k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
-              const int64_t* __restrict__ range_list, const int* __restrict__ rounds, const int* __restrict__ n_rounds,
-              int n_nodes, int64_t n_edges, int* __restrict__ perm, int64_t* __restrict__ out) {
+              const int64_t* __restrict__ range_list, const int* __restrict__ rounds, const int* __restrict__ round_ptr,
+              const int* __restrict__ n_rounds, int n_nodes, int64_t n_edges, int* __restrict__ perm,
+              int64_t* __restrict__ out) {
     __shared__ int sw[33];
     __shared__ int s_carry;
     const int r = blockIdx.x;
@@ -172,7 +177,7 @@ k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, in
     const int nr = n_rounds[r];
     if (k <= 0 || nr <= 0) return;
     int* pr = perm + start;
-    const int* rd = rounds + int64_t(r) * MAX_ROUNDS * 2;
+    const int* rd = rounds + 2 * int64_t(round_ptr[r]);
     const int a0 = rd[0];
     for (int i = threadIdx.x; i < k; i += blockDim.x) pr[i] = A[a0 + i];
     __syncthreads();
@@ -255,21 +260,24 @@ static int64_t bitmap_words(int64_t n_nodes) { return (n_nodes * n_nodes + 31) /
 
 struct NegWs {
     uint32_t* U;
-    int *flags, *A, *Apos, *perm, *rounds, *n_rounds, *chain_out;
+    int *flags, *A, *Apos, *perm, *rounds, *round_ptr, *n_rounds, *chain_out;
+    int round_cap;
     void* scan_ws;
 };
 static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t budget, void* base, NegWs* w) {
     Carver c(base);
     NegWs t;
     t.U = c.take<uint32_t>(budget + 3 * MT_N);
-    t.flags = c.take<int>(budget + 2);
-    t.A = c.take<int>(budget + 1);
-    t.Apos = c.take<int>(budget + 1);
+    t.flags = c.take<int>(budget + MT_N + 2);
+    t.A = c.take<int>(budget + MT_N + 2);
+    t.Apos = c.take<int>(budget + MT_N + 2);
     t.perm = c.take<int>(n_edges + 1);
-    t.rounds = c.take<int>(n_rel * MAX_ROUNDS * 2);
+    t.round_cap = int(n_rel * 8 + 65536);  // a relation whose pairs cover 99% of the cells needs ~1500 rounds
+    t.rounds = c.take<int>(size_t(t.round_cap) * 2);
+    t.round_ptr = c.take<int>(n_rel);
     t.n_rounds = c.take<int>(n_rel);
     t.chain_out = c.take<int>(4);
-    t.scan_ws = c.take<char>(scan_ws_bytes(budget + 1));
+    t.scan_ws = c.take<char>(scan_ws_bytes(budget + MT_N + 2));
     if (w) *w = t;
     return c.used() + 256;
 }
@@ -328,9 +336,9 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* member, const int64_t* r
     int rc = exclusive_scan_i32(w.flags, w.flags, n_words, w.scan_ws, s);
     if (rc) return rc;
     k_compact<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(w.U, mt_state + MT_N, n_words, mask, max_val, w.flags, w.A, w.Apos);
-    k_chain<<<1, 1024, 0, s>>>(w.A, w.flags + n_words, member, bitmap_words(n_nodes), range_list, (int)n_rel, w.rounds,
-                              w.n_rounds, w.chain_out, status);
-    k_materialize<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, bitmap_words(n_nodes), range_list, w.rounds, w.n_rounds,
+    k_chain<<<1, 1024, 0, s>>>(w.A, w.flags + n_words, member, bitmap_words(n_nodes), range_list, (int)n_rel, w.round_cap,
+                              w.rounds, w.round_ptr, w.n_rounds, w.chain_out, status);
+    k_materialize<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, bitmap_words(n_nodes), range_list, w.rounds, w.round_ptr, w.n_rounds,
                                                   (int)n_nodes, n_edges, w.perm, neg_edge_index);
     k_finalize<<<1, 256, 0, s>>>(w.U, w.Apos, w.chain_out, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");

@@ -341,6 +341,13 @@ using namespace tipb;
 
 extern "C" {
 
+int tipb_seg_aggregate(const void* plan, int64_t n_entries, int64_t n_nodes, int64_t n_rel, const float* feat,
+                       int64_t n_feat_rows, int f, float* out, void* stream) {
+    TIPB_CHECK_ARG(plan && feat && out, "seg_aggregate: NULL argument");
+    CsrView v = csr_view(plan, n_entries, n_nodes, n_rel);
+    return seg_aggregate_launch(v, feat, nullptr, nullptr, (int)n_feat_rows, f, out, (cudaStream_t)stream);
+}
+
 size_t tipb_rgcn_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel, int f_in, int f_out, int n_bases) {
     int64_t cap = n_nodes * n_rel;
     int64_t seg_cap = n_entries < cap ? n_entries : cap;

@@ -290,7 +290,7 @@ int tipb_typed_csr_build(const int64_t* edge_index, const int64_t* edge_type, co
     TIPB_CHECK_ARG(entries < (int64_t(1) << 31) - 2, "typed_csr_build: too many entries for int32 indexing");
     TIPB_CHECK_ARG(n_nodes * n_rel < (int64_t(1) << 32) - 1, "typed_csr_build: n_nodes*n_rel must fit 32 bits");
     TIPB_CHECK_ARG(n_edges == 0 || edge_index, "typed_csr_build: edge_index is NULL");
-    TIPB_CHECK_ARG(n_rel == 1 || edge_type || range_list, "typed_csr_build: need edge_type or range_list");
+    TIPB_CHECK_ARG(n_rel == 1 || n_edges == 0 || edge_type || range_list, "typed_csr_build: need edge_type or range_list");
     TIPB_CHECK_ARG(plan && plan_bytes >= tipb_typed_csr_bytes(entries, n_nodes, n_rel), "typed_csr_build: plan buffer too small");
     TIPB_CHECK_ARG(ws && ws_bytes >= tipb_typed_csr_workspace_bytes(entries, n_nodes, n_rel), "typed_csr_build: workspace too small");
     return tipb::csr_build(edge_index, edge_type, range_list, n_edges, n_nodes, n_other, n_rel, by_src, doubled,

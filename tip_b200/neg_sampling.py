@@ -134,8 +134,8 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
         if code == 0:
             return out
         if code & 2:
-            raise _lib.TipbError("negative sampling: a relation needed more than 64 retry rounds "
-                                 "(its positive pairs cover almost every cell)")
+            raise _lib.TipbError("negative sampling: the retry-round table overflowed "
+                                 "(some relation's positive pairs cover almost every cell)")
         st.copy_(saved)          # out of pre-generated words: rewind the stream and redo with a larger budget
         budget = budget * 2
         m.budget = budget

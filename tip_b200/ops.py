@@ -60,7 +60,7 @@ class TypedCSR(object):
         self.device = device
         L = lib()
         self.nbytes = L.tipb_typed_csr_bytes(self.n_entries, self.n_nodes, self.n_rel)
-        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
         self._layout, self.seg_cap = _lib.csr_layout(self.n_entries, self.n_nodes, self.n_rel)
         self._ws_bytes = L.tipb_typed_csr_workspace_bytes(self.n_entries, self.n_nodes, self.n_rel)
 
