@@ -1,0 +1,387 @@
+"""Benchmark of the TIP tri-graph encoder/decoder hot path (BASELINE.json metric:
+"TIP-cat train step ms & typed-edge msgs/s at 1/2/4/8 B200; % HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+One "step" = one full-batch training step of TIP-cat (tip.py:24-30): encoder forward, typed negative
+sampling, decoder + loss, backward, Adam -- on the synthetic polypharmacy-shape graph of SURVEY.md section 8(d)
+(645 drugs, 19,081 proteins, 861 relations, ~8.28 M directed typed D-D edges).
+value = typed-edge messages per second = 4 * E_directed / step_time (2 R-GCN layers + positive + negative
+decoder pass, forward count; backward and Adam are in the time, not in the count).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "typed_edge_msgs_per_s"
+UNIT = "msgs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mod", default="cat", choices=["cat", "add"])
+    ap.add_argument("--shape", default="polypharmacy", choices=["polypharmacy", "small"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--cpu-sample-relations", type=int, default=48)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_data(shape):
+    from tip_b200 import synth
+    if shape == "small":
+        return synth.make_tip_data(n_drug=200, n_prot=2000, n_rel=40, dd_undirected=60_000, pp_undirected=20_000,
+                                   pd_edges=2_000, seed=1111), "synthetic small (debug) shape"
+    return synth.make_tip_data(**synth.POLYPHARMACY, seed=1112), \
+        "TIP-cat train step, synthetic polypharmacy shape: 645 drugs, 19081 proteins, 861 relations"
+
+
+def settings_for(mod):
+    from tip_b200 import layers
+    if mod == "cat":
+        return layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
+    return layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=64, n_embed=64, n_hid1=32, n_hid2=16, num_base=32)
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_factory(data, mod, n_sample_rel):
+    """The reference's CPU path for one training step, as the structural oracle (op-for-op restatement of
+    src/layers.py + src/neg_sampling.py, incl. the per-relation Python loops), on the first `n_sample_rel`
+    relations of the workload (a full step costs ~9 minutes on 8 cores)."""
+    from oracle import neg_sampling_oracle as nso
+    from oracle import tip_oracle as to
+    from tip_b200 import layers
+    n_rel = min(n_sample_rel, int(data["n_dd_et"]))
+    rl = data["dd_train_range"][:n_rel].clone()
+    e_s = int(rl[-1, 1])
+    d = {"dd_train_idx": data["dd_train_idx"][:, :e_s].contiguous(), "dd_train_et": data["dd_train_et"][:e_s].contiguous(),
+         "dd_train_range": rl, "pp_train_indices": data["pp_train_indices"], "dp_edge_index": data["dp_edge_index"],
+         "d_norm": data["d_norm"]}
+    torch.manual_seed(1111)
+    s = settings_for(mod)
+    enc = layers.FMEncoder("cpu", data["n_drug_feat"], n_rel, data["n_prot"], data["n_prot"], data["n_drug"],
+                           s.prot_drug_dim, s.num_base, s.n_embed, s.n_hid1, s.n_hid2, mod=mod)
+    dec = layers.MultiInnerProductDecoder(s.n_hid2, n_rel)
+    params = {"encoder." + n: p.detach().clone().requires_grad_(True) for n, p in enc.named_parameters()}
+    params["decoder.weight"] = dec.weight.detach().clone().requires_grad_(True)
+    orc = to.TipOracle(params, data["n_drug"], data["n_prot"], mod=mod, structural=True)
+    opt = torch.optim.Adam(list(params.values()), lr=s.lr)
+    mt = nso.MT19937(1111)
+    pos_np, rl_np = d["dd_train_idx"].numpy(), rl.numpy()
+
+    def step():
+        opt.zero_grad()
+        neg = torch.from_numpy(nso.typed_negative_sampling(mt, pos_np, data["n_drug"], rl_np))
+        loss, _ = orc.loss(d, neg)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step, e_s, n_rel
+
+
+def time_cpu_reference(data, mod, n_sample_rel, steps, warmup):
+    step, e_s, n_rel = cpu_reference_step_factory(data, mod, n_sample_rel)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": 4.0 * e_s / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {n_rel} of {int(data['n_dd_et'])} relations ({e_s} directed D-D edges) + full P-P/P-D graphs; "
+                      f"{steps} step(s) of structural oracle fwd+neg-sampling+bwd+Adam, {dt:.2f} s/step",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    data, workload = make_data(args.shape)
+    res = time_cpu_reference(data, args.mod, args.cpu_sample_relations, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "mod": args.mod, "sample": res["sample"]},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- B200 arm
+def count_library_launches(step_fn):
+    """kernels of libtipb200 (namespace tipb::) launched by one eager step, counted with CUPTI."""
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    mine = total = 0
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA and not ev.name.startswith("Memcpy") and not ev.name.startswith("Memset"):
+            total += 1
+            if "tipb" in ev.name:
+                mine += 1
+    return mine, total
+
+
+def measure_dominant_kernel(model, iters):
+    """CUDA-event timing of the layer-1 edge pass (k_seg_aggregate, F_in = 64) launched alone on the
+    current stream, L2 flushed between launches."""
+    from tip_b200 import _lib, ops
+    d = model.data
+    dev = model.device
+    n, r = d.n_drug, d.n_dd_et
+    plan = ops.cached_plan(d.dd_train_idx, n, r, range_list=d.dd_train_range, by_src=False)
+    f_in = model.encoder.rgcn1.in_channels
+    x = torch.randn(n, f_in, device=dev)
+    out = torch.empty(plan.seg_cap * f_in, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    times = []
+    for i in range(iters + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.tipb_seg_aggregate(plan.buf.data_ptr(), plan.n_entries, n, r, x.data_ptr(), n, f_in, out.data_ptr(),
+                                        _lib.stream()), "seg_aggregate")
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    S = int(plan.field("counts")[0])
+    e = plan.n_entries
+    alg_bytes = e * (4 + 4 * f_in) + S * 4 * f_in + 4 * (S + 1)      # index + gathered row per edge, H row per segment
+    compulsory = 4 * e + 4 * (S + 1) + 4 * n * f_in + 4 * S * f_in  # each distinct byte once
+    return statistics.mean(times), alg_bytes, compulsory, S
+
+
+def run_b200_arm(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from tip_b200 import layers, neg_sampling as ns
+
+    data, workload = make_data(args.shape)
+    e_total = int(data["dd_train_idx"].shape[1])
+    torch.manual_seed(1111)
+    ns.seed(1111, dev)
+    if world > 1:
+        from tip_b200 import parallel
+        model = parallel.ShardedTIP(settings_for(args.mod), dev, mod=args.mod, data=data, rank=rank, world=world)
+    else:
+        model = layers.TIP(settings_for(args.mod), dev, mod=args.mod, data=data)
+    opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = model(check_status=False)
+        loss.backward()
+        if world > 1:
+            model.sync_gradients()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up on a side stream (fills every cache / workspace; the recipe CUDA-graph capture needs)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(args.warmup, 3)):
+            loss_value = float(step().detach())
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert int(ns.last_status(dev)) == 0, "negative sampler ran out of pre-generated words"
+
+    graph = None
+    static_loss = None
+    if not args.no_graph:
+        try:
+            model.embeddings = None          # drop the last eager autograd graph before capturing
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step().detach()
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:  # capture is an optimisation; eager is the fallback (still the CUDA path)
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed, running eagerly: {exc}", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    run_step = (lambda: graph.replay()) if graph is not None else step
+
+    # ---- timed region: K steps, device events, max over ranks
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t)
+    assert int(ns.last_status(dev)) == 0
+    step_s = elapsed / args.steps
+    value = 4.0 * e_total / step_s
+
+    # ---- end-to-end: every step copies the step's inputs (the graph tensors, int64 as the reference API has them)
+    #      from pinned host memory, rebuilds every index structure from them, trains one step and reads the loss back
+    if static_loss is not None:
+        loss_value = float(static_loss)
+    e2e = None
+    if world == 1:
+        e2e = measure_e2e(model, opt, data, args.steps, e_total)
+    launches, launches_all = count_library_launches(step) if rank == 0 else (0, 0)
+
+    if rank == 0:
+        k_time, alg_bytes, compulsory, n_seg = measure_dominant_kernel(model, max(args.steps, 10))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / k_time / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_seg_aggregate<F=64> (R-GCN layer-1 edge pass)", "achieved": achieved,
+                    "peak": peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_us": k_time * 1e6,
+                    "algorithmic_bytes": alg_bytes, "compulsory_dram_bytes": compulsory,
+                    "compulsory_frac": compulsory / k_time / 1e9 / peak, "segments": n_seg,
+                    "note": "features are staged in shared memory: achieved counts gathered bytes (SURVEY 8d figure A), "
+                            "compulsory_frac counts each distinct DRAM byte once (figure B)"}
+        cpu = None
+        if not args.skip_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cpu = time_cpu_reference(data, args.mod, args.cpu_sample_relations, 1, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "mod": args.mod, "directed_dd_edges": e_total,
+                           "parallelism": "relations sharded over %d GPU(s), P-P/P-D replicated" % world,
+                           "cuda_graph": graph is not None, "neg_sampler": "MT19937 bit-exact (numpy-compatible)",
+                           "l2": "per-step working set (index arrays + sampler stream, >0.6 GB) exceeds the 126 MB L2; no flush"},
+                "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+                "all_cuda_kernels_per_step": launches_all, "loss": loss_value}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(model, opt, data, steps, e_total):
+    from tip_b200 import ops
+    dev = model.device
+    names = ("dd_train_idx", "dd_train_et", "dd_train_range", "pp_train_indices", "dp_edge_index", "d_norm")
+    host = {k: data[k].contiguous().pin_memory() for k in names}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d = model.data
+
+    def e2e_step():
+        for k in names:                       # host -> device, in place (bumps the tensor version => plans are rebuilt)
+            getattr(d, k).copy_(host[k], non_blocking=True)
+        ops.clear_plan_cache()
+        model.invalidate_graph_caches()
+        opt.zero_grad(set_to_none=True)
+        loss = model(check_status=False)
+        loss.backward()
+        opt.step()
+        return loss.item()                    # device -> host
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 4.0 * e_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "ms_per_step": dt * 1e3,
+            "what": "pinned-host graph tensors -> device, all typed CSRs / bitmaps rebuilt, one train step, loss.item()"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

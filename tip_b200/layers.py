@@ -350,8 +350,11 @@ class TIP(nn.Module):
         with torch.no_grad():   # the reference's warm-up encoder call (src/layers.py:319); builds and caches the plans
             self.embeddings = self._encode()
         self.decoder = MultiInnerProductDecoder(s.n_hid2, d.n_dd_et).to(self.device)
-        self._pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range,
-                                         by_src=False, doubled=True)
+
+    def invalidate_graph_caches(self):
+        """forget every cached index structure (after the graph tensors were overwritten in place)"""
+        self.encoder.pp_encoder.conv1._cache = None
+        self.encoder.pp_encoder.conv2._cache = None
 
     def _encode(self):
         d = self.data
@@ -368,8 +371,10 @@ class TIP(nn.Module):
         neg_index = typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range, check_status=check_status,
                                             out=self._neg_index)
         self._neg_plan.build(neg_index, range_list=d.dd_train_range)
+        pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False,
+                                   doubled=True)
         # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient
-        return ops.bce_loss(self.embeddings, self.decoder.weight, self._pos_plan, self._neg_plan)
+        return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan)
 
     def pred(self, dd_idx, dd_et):
         return self.decoder(self.embeddings, dd_idx, dd_et)

@@ -141,6 +141,17 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
         m.budget = budget
 
 
+def last_status(device=None):
+    """OR of the status words of all cached samplers on `device` (0 = every unchecked call had enough
+    pre-generated words).  One host synchronisation."""
+    device = _device_of(device)
+    code = 0
+    for m in _member_cache.values():
+        if m.status.device == device:
+            code |= int(m.status.item())
+    return code
+
+
 def negative_sampling(pos_edge_index, num_nodes):
     """src/neg_sampling.py:5-19 (single relation)."""
     e = pos_edge_index.shape[1]

@@ -99,6 +99,10 @@ class TypedCSR(object):
 _plan_cache = {}
 
 
+def clear_plan_cache():
+    _plan_cache.clear()
+
+
 def _tensor_key(t):
     return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
 
