@@ -241,6 +241,7 @@ def run_b200_arm(args):
         if world > 1:
             model.sync_gradients()
         opt.step()
+        ns.join_prefetch(dev)        # the next step's MT19937 words were generated on a side stream meanwhile
         return loss
 
     def barrier():

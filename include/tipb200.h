@@ -152,22 +152,38 @@ int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int
 
 /* ---------------------------------------------------------------- typed negative sampling
  * Replaces typed_negative_sampling (src/neg_sampling.py:5-26) bit for bit, including the legacy
- * numpy MT19937 stream behind np.random.choice, the retry loop's indexing quirk and the float32
- * row = perm / num_nodes.  `mt_state` is [624 key words, position] = 625 uint32 on the device,
- * interchangeable with numpy's RandomState.get_state()[1:3]; it is advanced in place.
- * `member` is the per-relation membership bitmap of the positive pairs (tipb_neg_bitmap_build). */
+ * numpy MT19937 stream behind np.random.choice (the reference seeds it at src/layers.py:14), the retry
+ * loop's indexing quirk and the float32 row = perm / num_nodes.
+ *   mt_state      [624 key words, position] = 625 uint32 on the device, interchangeable with numpy's
+ *                 RandomState.get_state()[1:3]; tipb_neg_sample advances it in place.
+ *   stream_words  the untempered MT19937 stream starting at the state's key block:
+ *                 [0,624) = the key block itself, then n_new further words (tipb_mt19937_generate).
+ *                 It depends on the state only, so the host may produce it ahead of time.
+ *   member        per-relation bitmaps of the positive pairs (+ their popcounts) from tipb_neg_bitmap_build.
+ *   table         per-relation brackets of the stream offsets (6 int64 per relation: lo, W, L, win_off, f_off, k)
+ *                 built ON THE HOST from host copies of range_list and the popcounts (tipb_neg_table_build,
+ *                 no CUDA call); totals[0..3] = sum_L, sum_W, highest accepted index a window may touch,
+ *                 expected accepted values consumed.
+ *   status        0 ok; bit0: stream_words too short; bit1: retry-round table overflow (exact mode);
+ *                 bit2: an offset left its bracket -- restore mt_state and call again with exact_mode = 1. */
+int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream);
+int64_t tipb_mt19937_stream_words(int64_t n_new); /* rounds n_new up to the generator's granularity (454) */
+int tipb_mt19937_generate(const uint32_t* mt_state, uint32_t* stream_words /* [624 + n_new] */, int64_t n_new,
+                          void* stream);
 size_t tipb_neg_bitmap_bytes(int64_t n_nodes, int64_t n_rel);
 int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges,
-                          int64_t n_nodes, int64_t n_rel, uint32_t* member, void* stream);
-/* budget_words = how many fresh MT19937 words to generate for this call (an upper bound on what the
- * rejection loops will consume; *status gets bit0 if it was too small, bit1 if a relation needed more
- * than ~n_rel*8+65536 retry rounds in total -- the caller then restores the state, enlarges the budget and calls again). */
-size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t budget_words);
-int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* member, const int64_t* range_list,
-                    int64_t n_edges, int64_t n_nodes, int64_t n_rel, int64_t budget_words,
+                          int64_t n_nodes, int64_t n_rel, uint32_t* member, int32_t* popcount /* [n_rel] */,
+                          void* stream);
+int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount_host, int64_t n_rel,
+                         int64_t n_nodes, double z_sigma, int64_t* table_host /* [n_rel*6] */,
+                         int64_t* totals_host /* [4] */);
+size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n_words, int64_t sum_l,
+                                       int64_t sum_w);
+int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* stream_words, int64_t n_words /* 624 + n_new */,
+                    const uint32_t* member, const int64_t* range_list, const int64_t* table /* device copy */,
+                    int64_t sum_l, int64_t sum_w, int64_t n_edges, int64_t n_nodes, int64_t n_rel, int exact_mode,
                     int64_t* neg_edge_index /* [2,n_edges] */, int32_t* status, void* ws, size_t ws_bytes,
                     void* stream);
-int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,9 +39,38 @@ def test_size_queries_need_no_gpu():
     layout, cap = _lib.csr_layout(e, n, r)
     assert cap == n * r and layout["counts"] == 0 and all(v % 256 == 0 for v in layout.values())
     assert L.tipb_rgcn_workspace_bytes(e, n, r, 64, 32, 32) >= n * r * 64 * 4
-    assert L.tipb_neg_sample_workspace_bytes(e, r, 13_000_000) > 13_000_000 * 16
+    assert L.tipb_neg_sample_workspace_bytes(e, r, 13_000_000, 11_000_000, 2_000_000) > 13_000_000 * 12
+    assert L.tipb_mt19937_stream_words(1000) == 1362 and L.tipb_mt19937_stream_words(908) == 908
     assert L.tipb_neg_bitmap_bytes(n, r) == ((n * n + 31) // 32) * 4 * r
     assert L.tipb_sort_workspace_bytes(e) > 0 and L.tipb_scan_workspace_bytes(e) > 0
+
+
+def test_neg_table_build_is_host_only_and_consistent():
+    import ctypes as C
+
+    import numpy as np
+    from tip_b200 import _lib
+    L = _lib.lib()
+    sizes = np.array([1500, 0, 2500, 40, 9000], dtype=np.int64)
+    ends = np.cumsum(sizes)
+    rl = np.ascontiguousarray(np.stack([ends - sizes, ends], axis=1))
+    pop = np.array([1400, 0, 2300, 40, 8000], dtype=np.int32)
+    table = np.zeros((5, 6), dtype=np.int64)
+    totals = np.zeros(4, dtype=np.int64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(L.tipb_neg_table_build(vp(rl), vp(pop), 5, 101, 7.0, vp(table), vp(totals)), "table")
+    lo, W, Lw, win_off, f_off, k = table.T
+    assert np.array_equal(k, sizes)
+    assert lo[0] == 0 and np.all(np.diff(lo) >= 0)
+    assert np.all(W >= 1) and np.all((Lw >= W + k) | (k == 0))
+    assert np.array_equal(win_off, np.concatenate([[0], np.cumsum(Lw)[:-1]]))
+    assert np.array_equal(f_off, np.concatenate([[0], np.cumsum(W)[:-1]]))
+    assert totals[0] == Lw.sum() and totals[1] == W.sum() and totals[2] >= (lo + Lw).max()
+    # expected offsets sit inside the brackets: relation r starts near sum(k) + sum(k d/(1-d))
+    d = pop / 101.0 ** 2
+    mean = np.concatenate([[0], np.cumsum(sizes * d / (1 - d))[:-1]])
+    start = np.concatenate([[0], ends[:-1]]) + mean
+    assert np.all(lo <= start) and np.all(start <= lo + W)
 
 
 def test_argument_errors_are_reported_not_thrown():

@@ -232,6 +232,7 @@ def test_negative_sampling_seed_and_numpy_handover():
     from oracle import neg_sampling_oracle as nso
     from tip_b200 import neg_sampling as ns
     d = dev()
+    ns._rng.pop(d.index, None)       # forget the stream buffer earlier tests grew
     ns.seed(1111, d)
     rs = np.random.RandomState(1111)
     st = ns.get_state(d)
@@ -245,11 +246,33 @@ def test_negative_sampling_seed_and_numpy_handover():
     ref = nso.typed_negative_sampling(mt, pairs, n, rl)
     pos_t, rl_t = T(pairs, d), T(rl, d)
     m = ns._membership(pos_t, n, rl_t)
-    m.budget = 700
+    m.n_new = 908
     out = ns.typed_negative_sampling(pos_t, n, rl_t)
+    assert m.n_new > 908, "the short stream must have triggered the out-of-words retry"
     assert np.array_equal(out.cpu().numpy(), ref)
     st = ns.get_state(d)
     assert np.array_equal(st[1], mt.key) and st[2] == mt.pos
+    # brackets of zero width: the walk leaves them, the exact sequential path must give the same pairs
+    ns.seed(1111, d)
+    old_z, ns.Z_SIGMA = ns.Z_SIGMA, 0.0
+    try:
+        pos2 = pos_t.clone()
+        m2 = ns._membership(pos2, n, rl_t)
+        m2.table[:, 1] = 1                       # W = 1 everywhere
+        out2 = ns.typed_negative_sampling(pos2, n, rl_t)
+    finally:
+        ns.Z_SIGMA = old_z
+    assert np.array_equal(out2.cpu().numpy(), ref)
+    st = ns.get_state(d)
+    assert np.array_equal(st[1], mt.key) and st[2] == mt.pos
+    # with prefetch off the result is the same
+    ns.seed(1111, d)
+    ns.set_prefetch(False)
+    try:
+        out3 = ns.typed_negative_sampling(pos_t, n, rl_t)
+    finally:
+        ns.set_prefetch(True)
+    assert np.array_equal(out3.cpu().numpy(), ref)
     # hand the stream to numpy and continue there
     np.random.set_state(st)
     assert np.array_equal(np.random.choice(n * n, 50), mt.choice(n * n, 50))

@@ -13,16 +13,23 @@
 // outputs, AND with (2^ceil(log2 n) - 1), drop values > n-1, until k are kept.  The stream is shared
 // by all relations, so relation r starts where relation r-1 (including its retries) stopped.
 //
-// Pipeline (all on `stream`, no host synchronisation):
-//   k_mt_generate   one CTA runs the MT19937 recurrence S[n+624] = S[n+397] ^ g(S[n], S[n+1]); thread t
-//                   owns outputs 624 + t + 227p, so S[n+397] is its own previous value (register) and the
-//                   other two operands were written >= 2 phases ago (one barrier per two phases)
-//   k_accept_flags / scan / k_compact   masked-rejection as a stream compaction -> accepted stream A
-//   k_chain         one CTA walks the relations in order: per retry round, count members of A[...] in the
-//                   relation's positive-pair bitmap; records every round's (start, length)
-//   k_materialize   one CTA per relation replays the rounds (stable compaction of hit positions) and
-//                   writes the int64 [2,E] result
-//   k_finalize      advances the caller's MT19937 state to exactly where numpy's would be
+// How this becomes a parallel program
+//   1. The raw MT19937 words do not depend on the data: tipb_mt19937_generate produces them ahead of
+//      time (the Python host overlaps it with the rest of the training step on a side stream).
+//   2. Masked rejection is a stream compaction (flags -> scan -> scatter): accepted stream A.
+//   3. A relation's retry loop ends when a whole round has no positive pair, which is exactly when the
+//      relation has consumed its k_r-th NON-member value of A.  So the start offset of relation r+1 is
+//      o_{r+1} = 1 + position of the k_r-th non-member (w.r.t. relation r's bitmap) at or after o_r.
+//      o_r is only known to within the fluctuation of the retry counts, so every relation evaluates that
+//      map for a whole bracket of candidate offsets in parallel (k_window_scan; brackets are
+//      mean +- z*sigma of a negative-binomial model, built on the host once per graph by
+//      tipb_neg_table_build) and one thread then walks the chain of table lookups.
+//      A bracket miss is detected and reported (status bit 2); the caller reruns in exact mode
+//      (k_chain_exact: one CTA walks the relations and counts round by round).
+//   4. With o_r known, round 0 and round 1 of every relation are independent per draw (k_materialize_main),
+//      the geometrically smaller rounds >= 2 are replayed by one warp per relation (k_materialize_fixup).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace tipb {
@@ -30,8 +37,9 @@ namespace tipb {
 constexpr int MT_N = 624, MT_M = 397, MT_LAG = MT_N - MT_M;  // 227
 constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MATRIX_A = 0x9908b0dfu;
 constexpr int RING = 2048;
+constexpr int TAB = 6;  // per-relation table row: lo, W, L, win_off, f_off, k
 
-enum { NEG_STATUS_OUT_OF_WORDS = 1, NEG_STATUS_TOO_MANY_ROUNDS = 2 };
+enum { NEG_STATUS_OUT_OF_WORDS = 1, NEG_STATUS_TOO_MANY_ROUNDS = 2, NEG_STATUS_BRACKET_MISS = 4 };
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= y >> 11;
@@ -42,7 +50,7 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 }
 __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
     uint32_t y = (a & MT_UPPER) | (b & MT_LOWER);
-    return (y >> 1) ^ ((b & 1u) ? MT_MATRIX_A : 0u);
+    return (y >> 1) ^ (MT_MATRIX_A & (0u - (b & 1u)));
 }
 
 __global__ void k_mt_seed(uint32_t* __restrict__ state, uint32_t seed) {
@@ -56,33 +64,37 @@ __global__ void k_mt_seed(uint32_t* __restrict__ state, uint32_t seed) {
     }
 }
 
-// U[0..624) = current key; U[624 + i] = i-th further word of the untempered stream, for i < n_new.
+// U[0..624) = current key block; U[624 + i] = i-th further word of the untempered stream, i < n_new
+// (n_new a multiple of 454).  One CTA runs S[n+624] = S[n+397] ^ mix(S[n], S[n+1]): thread t owns the
+// outputs with n = t mod 227, so S[n+397] is its own previous output (a register) and the two mix operands
+// were written at least two phases (454 words) earlier -> one barrier per two phases.
 __global__ void __launch_bounds__(256) k_mt_generate(const uint32_t* __restrict__ state, uint32_t* __restrict__ U,
-                                                     int64_t n_new) {
+                                                     int n_new) {
     __shared__ uint32_t ring[RING];
     const int t = threadIdx.x;
-    for (int i = t; i < MT_N; i += blockDim.x) {
-        uint32_t v = state[i];
+    for (int i = t; i < MT_N; i += 256) {
+        const uint32_t v = state[i];
         ring[i] = v;
         U[i] = v;
     }
     __syncthreads();
-    const int64_t n_phases = (n_new + MT_LAG - 1) / MT_LAG;
-    uint32_t prev = t < MT_LAG ? ring[MT_M + t] : 0u;  // S[397 + t]
-    for (int64_t p = 0; p < n_phases; ++p) {
-        if (t < MT_LAG) {
-            const int64_t n = t + MT_LAG * p;  // produces S[n + 624]
-            const uint32_t a = ring[n & (RING - 1)], b = ring[(n + 1) & (RING - 1)];
-            const uint32_t v = prev ^ mt_mix(a, b);
-            ring[(n + MT_N) & (RING - 1)] = v;
-            if (n < n_new) U[n + MT_N] = v;
-            prev = v;
+    const bool active = t < MT_LAG;  // threads 227..255 only take part in the barriers
+    uint32_t prev = active ? ring[MT_M + t] : 0u;
+    uint32_t* out = U + MT_N;
+    const int n_iter = n_new / (2 * MT_LAG);
+    int n = active ? t : 0;
+    for (int it = 0; it < n_iter; ++it, n += 2 * MT_LAG) {
+        if (active) {
+            const uint32_t v0 = prev ^ mt_mix(ring[n & (RING - 1)], ring[(n + 1) & (RING - 1)]);
+            ring[(n + MT_N) & (RING - 1)] = v0;
+            out[n] = v0;
+            const int n1 = n + MT_LAG;
+            const uint32_t v1 = v0 ^ mt_mix(ring[n1 & (RING - 1)], ring[(n1 + 1) & (RING - 1)]);
+            ring[(n1 + MT_N) & (RING - 1)] = v1;
+            out[n1] = v1;
+            prev = v1;
         }
-        // operands of phase p+1 were produced in phases <= p-1 (S[n], S[n+1] with n+1 <= 227(p+2)-1+1 < 624+227p
-        // only when p >= ... ) -- the first phases read the seed block, later ones need data two phases old,
-        // except S[n+1] of thread 226 at phase p, which is S[227(p+1)]: produced by thread 0 in phase p+1-3+... ;
-        // a barrier after every phase whose successor could read fresh data keeps this simple and safe:
-        if ((p & 1) || p < 4) __syncthreads();
+        __syncthreads();
     }
 }
 
@@ -112,18 +124,214 @@ __device__ __forceinline__ bool is_member(const uint32_t* __restrict__ bits, int
     return (bits[key >> 5] >> (key & 31)) & 1u;
 }
 
-// rounds[round_ptr[r] + q] = (start, len) in the accepted stream, q < n_rounds[r] (one flat table for all
-// relations, `round_cap` entries); chain_out[0] = accepted values consumed
+__device__ __forceinline__ void write_pair(int64_t* __restrict__ out, int64_t n_edges, int64_t e, int p, int n_nodes,
+                                           float fn) {
+    const float row = __fdiv_rn(__int2float_rn(p), fn);  // float32 true division, as torch does for perm / N
+    out[e] = (long long)row;                             // .long(): truncation toward zero
+    out[n_edges + e] = (long long)(p % n_nodes);
+}
+
+// ================================================================================================
+// fast path
+// ================================================================================================
+// One CTA per relation.  Window = accepted-stream positions [lo, lo+L).  Produces
+//   NHI[win_off + x] = number of non-members among window entries 0..x (inclusive)
+//   PR [win_off + m] = window index of the (m+1)-th non-member
+//   F  [f_off + x]   = next relation's start offset if this relation starts at lo + x   (x < W; -1: window too short)
 __global__ void __launch_bounds__(1024)
-k_chain(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
-        int64_t words_per_rel, const int64_t* __restrict__ range_list, int n_rel, int round_cap,
-        int* __restrict__ rounds, int* __restrict__ round_ptr, int* __restrict__ n_rounds, int* __restrict__ chain_out,
-        int* __restrict__ status) {
+k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
+              int64_t words_per_rel, const int64_t* __restrict__ table, int* __restrict__ NHI, int* __restrict__ PR,
+              int* __restrict__ F) {
+    __shared__ int sw[33];
+    __shared__ int s_carry;
+    const int r = blockIdx.x;
+    const int64_t* tb = table + int64_t(r) * TAB;
+    const int lo = int(tb[0]), W = int(tb[1]), L = int(tb[2]), k = int(tb[5]);
+    const int64_t win_off = tb[3], f_off = tb[4];
+    if (k == 0) {
+        for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = lo + x;
+        return;
+    }
+    const uint32_t* bits = member + int64_t(r) * words_per_rel;
+    const int n_acc = *n_accepted_ptr;
+    int* nhi = NHI + win_off;
+    int* pr = PR + win_off;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    constexpr int ITEMS = 4;
+    for (int base = 0; base < L; base += 1024 * ITEMS) {
+        const int x0 = base + threadIdx.x * ITEMS;
+        int nh[ITEMS];
+        int local = 0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int x = x0 + i, j = lo + x;
+            nh[i] = (x < L && j < n_acc && !is_member(bits, A[j])) ? 1 : 0;
+            local += nh[i];
+        }
+        // block-wide exclusive scan of `local`
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FULL, incl, o);
+            if (lane_id() >= o) incl += y;
+        }
+        if (lane_id() == 31) sw[warp_id()] = incl;
+        __syncthreads();
+        if (warp_id() == 0) {
+            int v = sw[lane_id()], xs = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(FULL, xs, o);
+                if (lane_id() >= o) xs += y;
+            }
+            sw[lane_id()] = xs - v;
+            if (lane_id() == 31) sw[32] = xs;
+        }
+        __syncthreads();
+        int run = s_carry + sw[warp_id()] + incl - local;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int x = x0 + i;
+            if (x < L) {
+                if (nh[i]) pr[run] = x;
+                run += nh[i];
+                nhi[x] = run;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += sw[32];
+        __syncthreads();
+    }
+    const int total = s_carry;
+    for (int x = threadIdx.x; x < W; x += 1024) {
+        const int rb = x == 0 ? 0 : nhi[x - 1];
+        const int target = rb + k;
+        F[f_off + x] = target <= total ? lo + pr[target - 1] + 1 : -1;
+    }
+}
+
+// one thread follows o_{r+1} = F_r[o_r - lo_r]
+__global__ void __launch_bounds__(256)
+k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n_rel, int* __restrict__ off,
+             int* __restrict__ chain_out, int* __restrict__ status) {
+    extern __shared__ int s_tab[];  // per relation: lo, W, f_off (fits 32 bits), k
+    for (int i = threadIdx.x; i < n_rel; i += blockDim.x) {
+        const int64_t* tb = table + int64_t(i) * TAB;
+        s_tab[4 * i] = int(tb[0]);
+        s_tab[4 * i + 1] = int(tb[1]);
+        s_tab[4 * i + 2] = int(tb[4]);
+        s_tab[4 * i + 3] = int(tb[5]);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int o = 0;
+    int r = 0;
+    for (; r < n_rel; ++r) {
+        off[r] = o;
+        if (s_tab[4 * r + 3] == 0) continue;
+        const int x = o - s_tab[4 * r];
+        if (x < 0 || x >= s_tab[4 * r + 1]) {
+            atomicOr(status, NEG_STATUS_BRACKET_MISS);
+            break;
+        }
+        const int nxt = F[s_tab[4 * r + 2] + x];
+        if (nxt < 0) {
+            atomicOr(status, NEG_STATUS_OUT_OF_WORDS);
+            break;
+        }
+        o = nxt;
+    }
+    for (int q = r; q < n_rel; ++q) off[q] = -1;  // relations that could not be placed (r == n_rel: none)
+    chain_out[0] = o;
+}
+
+// rounds 0 and 1, one thread per draw
+__global__ void __launch_bounds__(256)
+k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
+                   const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
+                   const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
+                   int64_t* __restrict__ out) {
+    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    int lo_r = 0, hi_r = n_rel - 1;
+    while (lo_r < hi_r) {
+        int mid = (lo_r + hi_r + 1) >> 1;
+        if (range_list[2 * mid] <= e) lo_r = mid; else hi_r = mid - 1;
+    }
+    const int r = lo_r;
+    const int64_t start = range_list[2 * r];
+    if (e >= range_list[2 * r + 1]) return;
+    const int o = off[r];
+    if (o < 0) return;
+    const int64_t* tb = table + int64_t(r) * TAB;
+    const int lo = int(tb[0]), k = int(tb[5]);
+    const int* nhi = NHI + tb[3];
+    const uint32_t* bits = member + int64_t(r) * words_per_rel;
+    const int i = int(e - start);
+    int p = A[o + i];
+    if (is_member(bits, p)) {
+        const int x0 = o - lo;
+        const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
+        const int hits_incl = (i + 1) - (nhi[x0 + i] - rb);
+        p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
+    }
+    write_pair(out, n_edges, e, p, n_nodes, float(n_nodes));
+}
+
+// rounds >= 2, one warp per relation
+__global__ void __launch_bounds__(256)
+k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
+                    const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
+                    const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
+                    int64_t* __restrict__ out) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rel) return;
+    const int lane = lane_id();
+    const int o = off[r];
+    const int64_t* tb = table + int64_t(r) * TAB;
+    const int lo = int(tb[0]), k = int(tb[5]);
+    if (o < 0 || k == 0) return;
+    const int* nhi = NHI + tb[3];
+    const uint32_t* bits = member + int64_t(r) * words_per_rel;
+    const int64_t start = range_list[2 * r];
+    const int x0 = o - lo;
+    const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
+    int c_prev = k - (nhi[x0 + k - 1] - rb);  // size of round 1 = hits of round 0
+    int s_prev = o + k;                        // round 1 = A[s_prev, s_prev + c_prev)
+    const float fn = float(n_nodes);
+    while (c_prev > 0) {
+        const int s_cur = s_prev + c_prev;
+        int c = 0;
+        for (int base = 0; base < c_prev; base += 32) {
+            const int p = base + lane;
+            const bool hit = p < c_prev && is_member(bits, A[s_prev + p]);
+            const unsigned bal = __ballot_sync(FULL, hit);
+            if (hit) {
+                const int t = c + __popc(bal & ((1u << lane) - 1u));
+                write_pair(out, n_edges, start + p, A[s_cur + t], n_nodes, fn);  // perm[rest] = tmp; rest indexes tmp_{q-1}
+            }
+            c += __popc(bal);
+        }
+        s_prev = s_cur;
+        c_prev = c;
+    }
+}
+
+// ================================================================================================
+// exact (sequential) path: no brackets, used when the fast path reports a bracket miss
+// ================================================================================================
+// rounds[round_ptr[r] + q] = (start, len) in the accepted stream, q < n_rounds[r]
+__global__ void __launch_bounds__(1024)
+k_chain_exact(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
+              int64_t words_per_rel, const int64_t* __restrict__ range_list, int n_rel, int round_cap,
+              int* __restrict__ rounds, int* __restrict__ round_ptr, int* __restrict__ n_rounds,
+              int* __restrict__ chain_out, int* __restrict__ status) {
     __shared__ int sw[32];
     __shared__ int s_total;
     const int n_acc = *n_accepted_ptr;
     int base = 0;
-    int used = 0;  // entries of the flat round table handed out so far
+    int used = 0;
     for (int r = 0; r < n_rel; ++r) {
         const uint32_t* bits = member + int64_t(r) * words_per_rel;
         int n = int(range_list[2 * r + 1] - range_list[2 * r]);
@@ -133,7 +341,7 @@ k_chain(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const
             if (base + n > n_acc || used >= round_cap) {
                 if (threadIdx.x == 0) atomicOr(status, base + n > n_acc ? NEG_STATUS_OUT_OF_WORDS : NEG_STATUS_TOO_MANY_ROUNDS);
                 n = 0;
-                base = n_acc;  // poison: every later relation fails the same way
+                base = n_acc;
                 break;
             }
             if (threadIdx.x == 0) {
@@ -162,12 +370,11 @@ k_chain(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const
     if (threadIdx.x == 0) chain_out[0] = base;
 }
 
-// one CTA per relation: replay the rounds, write int64 pairs
 __global__ void __launch_bounds__(256)
-k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
-              const int64_t* __restrict__ range_list, const int* __restrict__ rounds, const int* __restrict__ round_ptr,
-              const int* __restrict__ n_rounds, int n_nodes, int64_t n_edges, int* __restrict__ perm,
-              int64_t* __restrict__ out) {
+k_materialize_exact(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
+                    const int64_t* __restrict__ range_list, const int* __restrict__ rounds,
+                    const int* __restrict__ round_ptr, const int* __restrict__ n_rounds, int n_nodes, int64_t n_edges,
+                    int* __restrict__ perm, int64_t* __restrict__ out) {
     __shared__ int sw[33];
     __shared__ int s_carry;
     const int r = blockIdx.x;
@@ -181,7 +388,6 @@ k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, in
     const int a0 = rd[0];
     for (int i = threadIdx.x; i < k; i += blockDim.x) pr[i] = A[a0 + i];
     __syncthreads();
-    // round q >= 1: tmp_q = A[rd[2q] ...], positions = ascending hit positions inside tmp_{q-1}
     for (int q = 1; q < nr; ++q) {
         const int prev_start = rd[2 * (q - 1)], prev_len = rd[2 * (q - 1) + 1];
         const int cur_start = rd[2 * q];
@@ -190,7 +396,6 @@ k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, in
         for (int base = 0; base < prev_len; base += blockDim.x) {
             const int i = base + threadIdx.x;
             const int hit = (i < prev_len && is_member(bits, A[prev_start + i])) ? 1 : 0;
-            // block-wide exclusive scan of `hit` (ballot inside the warp, then across warps)
             const unsigned bal = __ballot_sync(FULL, hit);
             const int in_warp = __popc(bal & ((1u << lane_id()) - 1u));
             if (lane_id() == 0) sw[warp_id()] = __popc(bal);
@@ -215,14 +420,10 @@ k_materialize(const int* __restrict__ A, const uint32_t* __restrict__ member, in
     }
     __syncthreads();
     const float fn = float(n_nodes);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const int p = pr[i];
-        const float row = __fdiv_rn(__int2float_rn(p), fn);  // float32 true division, as torch does
-        out[start + i] = (long long)row;                       // .long(): truncation
-        out[n_edges + start + i] = (long long)(p % n_nodes);
-    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) write_pair(out, n_edges, start + i, pr[i], n_nodes, fn);
 }
 
+// ================================================================================================
 __global__ void __launch_bounds__(256)
 k_finalize(const uint32_t* __restrict__ U, const int* __restrict__ Apos, const int* __restrict__ chain_out,
            uint32_t* __restrict__ state) {
@@ -256,28 +457,48 @@ __global__ void k_bitmap_build(const int64_t* __restrict__ pos_edge_index, const
     atomicOr(&member[int64_t(lo) * words_per_rel + (key >> 5)], 1u << (key & 31));
 }
 
+__global__ void __launch_bounds__(256)
+k_bitmap_popcount(const uint32_t* __restrict__ member, int64_t words_per_rel, int* __restrict__ counts) {
+    __shared__ int sw[8];
+    const uint32_t* bits = member + int64_t(blockIdx.x) * words_per_rel;
+    int c = 0;
+    for (int64_t i = threadIdx.x; i < words_per_rel; i += 256) c += __popc(bits[i]);
+    c = warp_sum_i(c);
+    if (lane_id() == 0) sw[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += sw[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
 static int64_t bitmap_words(int64_t n_nodes) { return (n_nodes * n_nodes + 31) / 32; }
 
 struct NegWs {
-    uint32_t* U;
-    int *flags, *A, *Apos, *perm, *rounds, *round_ptr, *n_rounds, *chain_out;
+    int *flags, *A, *Apos, *NHI, *PR, *F, *off, *chain_out;
+    int *perm, *rounds, *round_ptr, *n_rounds;
     int round_cap;
     void* scan_ws;
 };
-static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t budget, void* base, NegWs* w) {
+static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t n_words, int64_t sum_l, int64_t sum_w, void* base,
+                            NegWs* w) {
     Carver c(base);
     NegWs t;
-    t.U = c.take<uint32_t>(budget + 3 * MT_N);
-    t.flags = c.take<int>(budget + MT_N + 2);
-    t.A = c.take<int>(budget + MT_N + 2);
-    t.Apos = c.take<int>(budget + MT_N + 2);
+    t.flags = c.take<int>(n_words + 2);
+    t.A = c.take<int>(n_words + 2);
+    t.Apos = c.take<int>(n_words + 2);
+    t.NHI = c.take<int>(sum_l + 1);
+    t.PR = c.take<int>(sum_l + 1);
+    t.F = c.take<int>(sum_w + 1);
+    t.off = c.take<int>(n_rel + 1);
+    t.chain_out = c.take<int>(4);
     t.perm = c.take<int>(n_edges + 1);
     t.round_cap = int(n_rel * 8 + 65536);  // a relation whose pairs cover 99% of the cells needs ~1500 rounds
     t.rounds = c.take<int>(size_t(t.round_cap) * 2);
-    t.round_ptr = c.take<int>(n_rel);
-    t.n_rounds = c.take<int>(n_rel);
-    t.chain_out = c.take<int>(4);
-    t.scan_ws = c.take<char>(scan_ws_bytes(budget + MT_N + 2));
+    t.round_ptr = c.take<int>(n_rel + 1);
+    t.n_rounds = c.take<int>(n_rel + 1);
+    t.scan_ws = c.take<char>(scan_ws_bytes(n_words + 2));
     if (w) *w = t;
     return c.used() + 256;
 }
@@ -295,52 +516,128 @@ int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream) {
     return TIPB_OK;
 }
 
+int64_t tipb_mt19937_stream_words(int64_t n_new) {
+    const int64_t q = 2 * MT_LAG;
+    return (n_new + q - 1) / q * q;
+}
+
+int tipb_mt19937_generate(const uint32_t* mt_state, uint32_t* stream_words, int64_t n_new, void* stream) {
+    TIPB_CHECK_ARG(mt_state && stream_words, "mt19937_generate: NULL argument");
+    TIPB_CHECK_ARG(n_new > 0 && n_new % (2 * MT_LAG) == 0 && n_new < (int64_t(1) << 31) - 4096,
+                   "mt19937_generate: n_new must be a positive multiple of 454 (use tipb_mt19937_stream_words)");
+    k_mt_generate<<<1, 256, 0, (cudaStream_t)stream>>>(mt_state, stream_words, (int)n_new);
+    TIPB_CHECK_LAUNCH("mt19937_generate");
+    return TIPB_OK;
+}
+
 size_t tipb_neg_bitmap_bytes(int64_t n_nodes, int64_t n_rel) { return size_t(bitmap_words(n_nodes)) * n_rel * 4; }
 
 int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_nodes,
-                          int64_t n_rel, uint32_t* member, void* stream) {
-    TIPB_CHECK_ARG(range_list && member && (n_edges == 0 || pos_edge_index), "neg_bitmap_build: NULL argument");
+                          int64_t n_rel, uint32_t* member, int32_t* popcount, void* stream) {
+    TIPB_CHECK_ARG(range_list && member && popcount && (n_edges == 0 || pos_edge_index), "neg_bitmap_build: NULL argument");
     TIPB_CHECK_ARG(n_nodes > 0 && n_nodes <= 46340, "neg_bitmap_build: n_nodes^2 must fit in int32");
     cudaStream_t s = (cudaStream_t)stream;
     TIPB_CHECK_CUDA(cudaMemsetAsync(member, 0, tipb_neg_bitmap_bytes(n_nodes, n_rel), s));
     if (n_edges > 0)
         k_bitmap_build<<<(unsigned)ceil_div(n_edges, 256), 256, 0, s>>>(pos_edge_index, range_list, n_edges, (int)n_nodes,
                                                                         (int)n_rel, bitmap_words(n_nodes), member);
+    if (n_rel > 0) k_bitmap_popcount<<<(unsigned)n_rel, 256, 0, s>>>(member, bitmap_words(n_nodes), popcount);
     TIPB_CHECK_LAUNCH("neg_bitmap_build");
     return TIPB_OK;
 }
 
-size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t budget_words) {
-    return neg_ws_layout(n_edges, n_rel, budget_words, nullptr, nullptr);
+// Host-only (no CUDA call): brackets of the per-relation start offsets from a negative-binomial model.
+//   relation r needs k_r non-members; with member density d_r the number of extra draws has mean k d/(1-d)
+//   and variance k d/(1-d)^2.  Offsets accumulate over relations, so do means and variances.
+int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount_host, int64_t n_rel, int64_t n_nodes,
+                         double z_sigma, int64_t* table_host, int64_t* totals_host) {
+    TIPB_CHECK_ARG(range_list_host && popcount_host && table_host && totals_host, "neg_table_build: NULL argument");
+    const double cells = double(n_nodes) * double(n_nodes);
+    const int64_t slack = 64;
+    double mean = 0.0, var = 0.0;
+    int64_t ksum = 0, sum_l = 0, sum_w = 0, max_index = 0;
+    for (int64_t r = 0; r < n_rel; ++r) {
+        const int64_t k = range_list_host[2 * r + 1] - range_list_host[2 * r];
+        TIPB_CHECK_ARG(k >= 0, "neg_table_build: negative relation size");
+        double d = double(popcount_host[r]) / cells;
+        if (d > 0.98) d = 0.98;
+        const double dev = z_sigma * sqrt(var);
+        int64_t lo_x = int64_t(floor(mean - dev)) - slack;
+        if (lo_x < 0) lo_x = 0;
+        const int64_t hi_x = int64_t(ceil(mean + dev)) + slack;
+        const int64_t lo = ksum + lo_x, W = hi_x - lo_x + 1;
+        const double ek = double(k) * d / (1.0 - d), vk = double(k) * d / ((1.0 - d) * (1.0 - d));
+        const int64_t L = k == 0 ? 0 : W + k + int64_t(ceil(ek + z_sigma * sqrt(vk))) + slack;
+        int64_t* tb = table_host + r * TAB;
+        tb[0] = lo; tb[1] = W; tb[2] = L; tb[3] = sum_l; tb[4] = sum_w; tb[5] = k;
+        sum_l += L;
+        sum_w += W;
+        if (lo + L > max_index) max_index = lo + L;
+        if (lo + W > max_index) max_index = lo + W;
+        ksum += k;
+        mean += ek;
+        var += vk;
+    }
+    TIPB_CHECK_ARG(max_index < (int64_t(1) << 31) - 4096 && sum_l < (int64_t(1) << 31) && sum_w < (int64_t(1) << 31),
+                   "neg_table_build: edge set too large for 32-bit stream offsets");
+    totals_host[0] = sum_l;
+    totals_host[1] = sum_w;
+    totals_host[2] = max_index;                        // accepted values the windows may touch
+    totals_host[3] = ksum + int64_t(ceil(mean));       // expected number of accepted values consumed
+    return TIPB_OK;
 }
 
-int tipb_neg_sample(uint32_t* mt_state, const uint32_t* member, const int64_t* range_list, int64_t n_edges,
-                    int64_t n_nodes, int64_t n_rel, int64_t budget_words, int64_t* neg_edge_index, int32_t* status,
-                    void* ws, size_t ws_bytes, void* stream) {
-    TIPB_CHECK_ARG(mt_state && member && range_list && neg_edge_index && status && ws, "neg_sample: NULL argument");
+size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n_words, int64_t sum_l, int64_t sum_w) {
+    return neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr);
+}
+
+int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words, const uint32_t* member,
+                    const int64_t* range_list, const int64_t* table, int64_t sum_l, int64_t sum_w, int64_t n_edges,
+                    int64_t n_nodes, int64_t n_rel, int exact_mode, int64_t* neg_edge_index, int32_t* status, void* ws,
+                    size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(mt_state && stream_words && member && range_list && neg_edge_index && status && ws,
+                   "neg_sample: NULL argument");
+    TIPB_CHECK_ARG(exact_mode || table, "neg_sample: the fast path needs the bracket table");
     TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample: n_nodes must be in [2, 46340]");
-    TIPB_CHECK_ARG(budget_words > 0 && budget_words < (int64_t(1) << 31) - 4096, "neg_sample: bad word budget");
-    TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, budget_words, nullptr, nullptr), "neg_sample: workspace too small");
+    TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample: bad stream length");
+    TIPB_CHECK_ARG(n_rel > 0 && n_rel * 16 <= 200 * 1024, "neg_sample: n_rel out of range");
+    TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
+                   "neg_sample: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     NegWs w;
-    neg_ws_layout(n_edges, n_rel, budget_words, ws, &w);
+    neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, ws, &w);
     const uint32_t max_val = uint32_t(n_nodes * n_nodes - 1);
     uint32_t mask = 1;
     while (mask < max_val) mask = (mask << 1) | 1u;
-    const int64_t n_words = budget_words + MT_N;  // candidate window = current key block + budget new words
     const int T = 256;
+    const int64_t wpr = bitmap_words(n_nodes);
+    int rc;
 
     TIPB_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
-    k_mt_generate<<<1, 256, 0, s>>>(mt_state, w.U, budget_words);
-    k_accept_flags<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(w.U, mt_state + MT_N, n_words, mask, max_val, w.flags);
-    int rc = exclusive_scan_i32(w.flags, w.flags, n_words, w.scan_ws, s);
-    if (rc) return rc;
-    k_compact<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(w.U, mt_state + MT_N, n_words, mask, max_val, w.flags, w.A, w.Apos);
-    k_chain<<<1, 1024, 0, s>>>(w.A, w.flags + n_words, member, bitmap_words(n_nodes), range_list, (int)n_rel, w.round_cap,
-                              w.rounds, w.round_ptr, w.n_rounds, w.chain_out, status);
-    k_materialize<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, bitmap_words(n_nodes), range_list, w.rounds, w.round_ptr, w.n_rounds,
-                                                  (int)n_nodes, n_edges, w.perm, neg_edge_index);
-    k_finalize<<<1, 256, 0, s>>>(w.U, w.Apos, w.chain_out, mt_state);
+    k_accept_flags<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
+    if ((rc = exclusive_scan_i32(w.flags, w.flags, n_words, w.scan_ws, s))) return rc;
+    k_compact<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
+                                                           w.A, w.Apos);
+    const int* n_acc = w.flags + n_words;
+    if (exact_mode) {
+        k_chain_exact<<<1, 1024, 0, s>>>(w.A, n_acc, member, wpr, range_list, (int)n_rel, w.round_cap, w.rounds,
+                                         w.round_ptr, w.n_rounds, w.chain_out, status);
+        k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
+                                                            w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
+    } else {
+        k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
+        const size_t smem = size_t(n_rel) * 16;
+        if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
+        k_chain_walk<<<1, 256, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
+        if (n_edges > 0)
+            k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
+                                                                           w.NHI, (int)n_rel, (int)n_nodes, n_edges,
+                                                                           neg_edge_index);
+        k_materialize_fixup<<<(unsigned)ceil_div(n_rel * 32, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
+                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,
+                                                                            neg_edge_index);
+    }
+    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");
     return TIPB_OK;
 }

@@ -8,7 +8,13 @@ global `np.random` stream seeded at import, src/layers.py:14).  `seed()`,
 `get_state()` and `set_state()` mirror `np.random.seed/get_state/set_state` so the
 stream can be handed over from numpy (e.g. after the reference's CPU-side
 `process_edges`, which consumes the same stream) and back.
+
+The raw MT19937 words depend on the state only, not on the graph, so after every call
+the words for the NEXT call are generated on a side stream while the caller goes on
+with the encoder/decoder work (`set_prefetch(False)` turns that off).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -16,8 +22,43 @@ from . import _lib
 from ._lib import check, lib, ptr, stream
 from .ops import _i64c, workspace
 
-_states = {}        # device index -> uint32 [625] tensor (624 key words + position)
-_member_cache = {}  # positive-pair bitmaps, keyed on the identity of (pos_edge_index, range_list)
+Z_SIGMA = 7.0          # half-width of the offset brackets, in standard deviations of the retry-count model
+_member_cache = {}     # positive-pair bitmaps + bracket tables, keyed on the identity of (pos_edge_index, range_list)
+_rng = {}              # device index -> _DeviceRng
+_prefetch = True
+
+
+class _DeviceRng(object):
+    def __init__(self, device):
+        self.device = device
+        self.state = torch.empty(625, dtype=torch.int32, device=device)   # 624 key words + position
+        self.words = None       # untempered stream generated from `state` (624 + n_new words)
+        self.n_new = 0
+        self.valid = False      # `words` matches the current state
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.ready = None       # event: the prefetch on `side` has finished
+        self.forked = False     # a prefetch is in flight that the caller's stream has not joined yet
+        with torch.cuda.device(device):
+            check(lib().tipb_mt19937_seed(ptr(self.state), 1111, stream()), "mt19937_seed")   # src/layers.py:14
+
+    def join(self):
+        """make the current stream wait for an in-flight prefetch (it reads `state` and writes `words`)"""
+        if self.forked:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            self.forked = False
+
+    def invalidate(self):
+        self.join()
+        self.valid = False
+
+    def generate(self, n_new):
+        L = lib()
+        n_new = int(L.tipb_mt19937_stream_words(int(n_new)))
+        if self.words is None or self.n_new < n_new:
+            self.join()
+            self.words = torch.empty(624 + n_new, dtype=torch.int32, device=self.device)
+            self.n_new = n_new
+        check(L.tipb_mt19937_generate(ptr(self.state), ptr(self.words), self.n_new, stream()), "mt19937_generate")
 
 
 def _device_of(device=None):
@@ -29,27 +70,37 @@ def _device_of(device=None):
     return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
 
 
-def _state(device):
-    st = _states.get(device.index)
-    if st is None:
-        st = torch.empty(625, dtype=torch.int32, device=device)
-        _states[device.index] = st
-        with torch.cuda.device(device):
-            check(lib().tipb_mt19937_seed(ptr(st), 1111, stream()), "mt19937_seed")   # src/layers.py:14
-    return st
+def _get_rng(device):
+    r = _rng.get(device.index)
+    if r is None:
+        r = _rng[device.index] = _DeviceRng(device)
+    return r
+
+
+def set_prefetch(flag):
+    """generate the next call's MT19937 words on a side stream right after each call (default on)"""
+    global _prefetch
+    _prefetch = bool(flag)
+
+
+def join_prefetch(device=None):
+    """Order the current stream after the in-flight prefetch.  Needed at the end of a CUDA-graph-captured
+    step (forked work must rejoin the capturing stream); harmless otherwise."""
+    _get_rng(_device_of(device)).join()
 
 
 def seed(value, device=None):
     """np.random.seed(value) for the device-side stream."""
     device = _device_of(device)
-    st = _state(device)
+    r = _get_rng(device)
+    r.invalidate()
     with torch.cuda.device(device):
-        check(lib().tipb_mt19937_seed(ptr(st), int(value) & 0xFFFFFFFF, stream()), "mt19937_seed")
+        check(lib().tipb_mt19937_seed(ptr(r.state), int(value) & 0xFFFFFFFF, stream()), "mt19937_seed")
 
 
 def get_state(device=None):
     """-> ('MT19937', key uint32[624], pos, 0, 0.0), the tuple np.random.set_state accepts."""
-    st = _state(_device_of(device)).cpu().numpy().view(np.uint32)
+    st = _get_rng(_device_of(device)).state.cpu().numpy().view(np.uint32)
     return ("MT19937", st[:624].copy(), int(st[624]), 0, 0.0)
 
 
@@ -59,11 +110,13 @@ def set_state(state, device=None):
     key = np.asarray(state[1], dtype=np.uint32)
     assert key.shape == (624,)
     host = np.concatenate([key, np.array([int(state[2])], dtype=np.uint32)]).view(np.int32)
-    _state(device).copy_(torch.from_numpy(host))
+    r = _get_rng(device)
+    r.invalidate()
+    r.state.copy_(torch.from_numpy(host))
 
 
 class _Membership(object):
-    """per-relation bitmap of the positive pairs + the host-side facts needed to size a call"""
+    """per-relation bitmaps of the positive pairs, their popcounts, and the bracket table"""
 
     def __init__(self, pos_edge_index, num_nodes, range_list):
         L = lib()
@@ -72,9 +125,8 @@ class _Membership(object):
         self.n_rel = int(range_list.shape[0])
         self.num_nodes = int(num_nodes)
         self.range_dev = _i64c(range_list.to(device=dev, dtype=torch.long))
-        rl = self.range_dev.cpu().numpy()                      # one-time host copy (setup, not per step)
-        sizes = (rl[:, 1] - rl[:, 0]).astype(np.float64)
-        cells = float(num_nodes) ** 2
+        rl = np.ascontiguousarray(self.range_dev.cpu().numpy())        # one-time host copy (setup, not per step)
+        sizes = rl[:, 1] - rl[:, 0]
         if self.n_rel and not (np.all(sizes >= 0) and np.all(rl[1:, 0] == rl[:-1, 1]) and rl[0, 0] == 0
                                and rl[-1, 1] == self.n_edges):
             raise ValueError("range_list must be the cumulative [start,end) table of src/utils.py:26-32")
@@ -82,16 +134,23 @@ class _Membership(object):
         if nbytes > (24 << 30):
             raise _lib.TipbError(f"positive-pair bitmaps would need {nbytes >> 30} GiB")
         self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)
+        popcount = torch.zeros(max(self.n_rel, 1), dtype=torch.int32, device=dev)
         check(L.tipb_neg_bitmap_build(ptr(_i64c(pos_edge_index)), ptr(self.range_dev), self.n_edges, num_nodes,
-                                      self.n_rel, ptr(self.member), stream()), "neg_bitmap_build")
-        # expected MT words: every kept draw costs 1/p_accept words, every relation redraws its collisions
+                                      self.n_rel, ptr(self.member), ptr(popcount), stream()), "neg_bitmap_build")
+        pop = np.ascontiguousarray(popcount.cpu().numpy())             # one-time host copy
+        table = np.zeros((max(self.n_rel, 1), 6), dtype=np.int64)
+        totals = np.zeros(4, dtype=np.int64)
+        check(L.tipb_neg_table_build(rl.ctypes.data_as(C.c_void_p), pop.ctypes.data_as(C.c_void_p), self.n_rel,
+                                     num_nodes, Z_SIGMA, table.ctypes.data_as(C.c_void_p),
+                                     totals.ctypes.data_as(C.c_void_p)), "neg_table_build")
+        self.table = torch.from_numpy(table).to(dev)
+        self.sum_l, self.sum_w, max_index = int(totals[0]), int(totals[1]), int(totals[2])
+        # MT words needed so that `max_index` accepted values exist: acceptance is Bernoulli(p_accept) per word
         bits = max(int(num_nodes * num_nodes - 1).bit_length(), 1)
-        p_accept = cells / float(1 << bits)
-        dens = np.minimum(sizes / cells, 0.98)
-        expect = float((sizes / (1.0 - dens)).sum()) / p_accept
-        self.budget = int(expect * 1.08 + 6.0 * np.sqrt(expect + 1.0) + 65536)
+        p_accept = float(num_nodes) ** 2 / float(1 << bits)
+        need = max_index / p_accept
+        self.n_new = int(need + Z_SIGMA * np.sqrt(need * (1.0 - p_accept) / p_accept + 1.0) + 4096)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.out = None
 
 
 def _membership(pos_edge_index, num_nodes, range_list):
@@ -116,34 +175,50 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
     num_nodes = int(num_nodes)
     dev = pos_edge_index.device
     m = _membership(pos_edge_index, num_nodes, range_list)
-    st = _state(dev)
     if out is None:
         out = torch.empty((2, m.n_edges), dtype=torch.long, device=dev)
     if m.n_edges == 0:
         return out
     L = lib()
-    budget = m.budget
+    rng = _get_rng(dev)
+    exact = 0
     while True:
-        saved = st.clone() if check_status else None
-        ws = workspace(L.tipb_neg_sample_workspace_bytes(m.n_edges, m.n_rel, budget), dev, "neg")
-        check(L.tipb_neg_sample(ptr(st), ptr(m.member), ptr(m.range_dev), m.n_edges, num_nodes, m.n_rel, budget,
-                                ptr(out), ptr(m.status), ptr(ws), ws.numel(), stream()), "neg_sample")
-        if not check_status:
-            return out
-        code = int(m.status.item())
+        rng.join()                                   # an earlier prefetch must be done before its words are read
+        if not rng.valid or rng.n_new < m.n_new:
+            rng.generate(max(m.n_new, rng.n_new))    # on the caller's stream (first call / state was reset)
+            rng.valid = True
+        saved = rng.state.clone() if check_status else None
+        n_words = 624 + rng.n_new
+        ws = workspace(L.tipb_neg_sample_workspace_bytes(m.n_edges, m.n_rel, n_words, m.sum_l, m.sum_w), dev, "neg")
+        check(L.tipb_neg_sample(ptr(rng.state), ptr(rng.words), n_words, ptr(m.member), ptr(m.range_dev), ptr(m.table),
+                                m.sum_l, m.sum_w, m.n_edges, num_nodes, m.n_rel, exact, ptr(out), ptr(m.status),
+                                ptr(ws), ws.numel(), stream()), "neg_sample")
+        rng.valid = False                            # the state moved on; `words` no longer starts at it
+        code = int(m.status.item()) if check_status else 0
         if code == 0:
-            return out
+            break
+        rng.state.copy_(saved)                       # rewind the stream and redo this call
         if code & 2:
             raise _lib.TipbError("negative sampling: the retry-round table overflowed "
                                  "(some relation's positive pairs cover almost every cell)")
-        st.copy_(saved)          # out of pre-generated words: rewind the stream and redo with a larger budget
-        budget = budget * 2
-        m.budget = budget
+        if code & 4:
+            exact = 1                                # an offset left its bracket: sequential exact path
+        if code & 1:
+            m.n_new = m.n_new * 2                    # not enough pre-generated words
+    if _prefetch:
+        # words for the next call, generated concurrently with whatever the caller does next
+        cur = torch.cuda.current_stream(dev)
+        rng.side.wait_stream(cur)
+        with torch.cuda.stream(rng.side):
+            rng.generate(max(m.n_new, rng.n_new))
+        rng.valid = True
+        rng.forked = True
+    return out
 
 
 def last_status(device=None):
     """OR of the status words of all cached samplers on `device` (0 = every unchecked call had enough
-    pre-generated words).  One host synchronisation."""
+    pre-generated words and stayed inside its brackets).  One host synchronisation."""
     device = _device_of(device)
     code = 0
     for m in _member_cache.values():
