@@ -279,15 +279,14 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
     write_pair(out, n_edges, e, p, n_nodes, float(n_nodes));
 }
 
-// rounds >= 2, one warp per relation
+// rounds >= 2, one CTA per relation
 __global__ void __launch_bounds__(256)
 k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                     const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                     const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
                     int64_t* __restrict__ out) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r = blockIdx.x;
     if (r >= n_rel) return;
-    const int lane = lane_id();
     const int o = off[r];
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), k = int(tb[5]);
@@ -300,19 +299,20 @@ k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ memb
     int c_prev = k - (nhi[x0 + k - 1] - rb);  // size of round 1 = hits of round 0
     int s_prev = o + k;                        // round 1 = A[s_prev, s_prev + c_prev)
     const float fn = float(n_nodes);
+    // Every round is a run of consecutive stream positions inside the window, so the rank of a hit inside its
+    // round follows from the non-member prefix counts; rounds are applied in order (later rounds overwrite).
     while (c_prev > 0) {
         const int s_cur = s_prev + c_prev;
-        int c = 0;
-        for (int base = 0; base < c_prev; base += 32) {
-            const int p = base + lane;
-            const bool hit = p < c_prev && is_member(bits, A[s_prev + p]);
-            const unsigned bal = __ballot_sync(FULL, hit);
-            if (hit) {
-                const int t = c + __popc(bal & ((1u << lane) - 1u));
+        const int xs = s_prev - lo;              // >= 1
+        const int nb = nhi[xs - 1];
+        for (int p = threadIdx.x; p < c_prev; p += blockDim.x) {
+            if (is_member(bits, A[s_prev + p])) {
+                const int t = (p + 1) - (nhi[xs + p] - nb) - 1;
                 write_pair(out, n_edges, start + p, A[s_cur + t], n_nodes, fn);  // perm[rest] = tmp; rest indexes tmp_{q-1}
             }
-            c += __popc(bal);
         }
+        const int c = c_prev - (nhi[xs + c_prev - 1] - nb);
+        __syncthreads();
         s_prev = s_cur;
         c_prev = c;
     }
@@ -633,7 +633,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,
                                                                            neg_edge_index);
-        k_materialize_fixup<<<(unsigned)ceil_div(n_rel * 32, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
+        k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                             w.NHI, (int)n_rel, (int)n_nodes, n_edges,
                                                                             neg_edge_index);
     }

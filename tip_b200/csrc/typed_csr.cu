@@ -210,11 +210,168 @@ static int bits_for(uint64_t max_value) {
     return b;
 }
 
+// ================================================================================================
+// Grouped build: when the edges arrive sorted by relation (range_list given -- the layout of
+// src/utils.py:35-65, and of every per-step negative sample), no global sort is needed.  The
+// (node, relation) segment sizes come from one histogram over the dense key space, their offsets
+// from one scan, and each relation is then placed by ONE CTA that walks its edges in input order
+// (per-warp counters + a per-node cursor in shared memory), which keeps the placement stable and
+// therefore bit-identical to the sort-based path.
+// ================================================================================================
+__device__ __forceinline__ bool grp_entry(const int64_t* __restrict__ edge_index, int64_t E, int64_t e, bool rev,
+                                          int by_src, int drop_loops, int n_nodes, int n_other, int& node,
+                                          int& other) {
+    const int64_t a = edge_index[e], b = edge_index[E + e];
+    const bool pick_a = (by_src != 0) != rev;
+    const int64_t nd = pick_a ? a : b, ot = pick_a ? b : a;
+    node = int(nd);
+    other = int(ot);
+    return nd >= 0 && nd < n_nodes && ot >= 0 && ot < n_other && !(drop_loops && nd == ot);
+}
+
+// status bit1: range_list is not the cumulative cover of [0, E)
+__global__ void k_grp_check_ranges(const int64_t* __restrict__ range_list, int n_rel, int64_t E, int* __restrict__ counts) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rel) return;
+    const int64_t s = range_list[2 * r], e = range_list[2 * r + 1];
+    const int64_t prev_end = r == 0 ? 0 : range_list[2 * r - 1];
+    bool ok = s == prev_end && e >= s && (r + 1 < n_rel || e == E);
+    if (!ok) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 2);
+}
+
+__global__ void __launch_bounds__(256)
+k_grp_count(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E, int doubled,
+            int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, int* __restrict__ cnt,
+            int* __restrict__ counts) {
+    const int r = blockIdx.y;
+    const int64_t start = range_list[2 * r], end = range_list[2 * r + 1];
+    bool bad = false;
+    for (int64_t e = start + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < end; e += int64_t(gridDim.x) * blockDim.x) {
+        for (int dir = 0; dir <= doubled; ++dir) {
+            int node, other;
+            if (grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, other))
+                atomicAdd(&cnt[int64_t(node) * n_rel + r], 1);
+            else if (!(drop_loops && node == other))
+                bad = true;
+        }
+    }
+    if (bad) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 1);
+}
+
+constexpr int GRP_ROUNDS = 16;
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E, int doubled,
+              int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, const int* __restrict__ seg_start,
+              int* __restrict__ eid, int* __restrict__ other_out) {
+    extern __shared__ int sm_i[];
+    int* wh = sm_i;                        // [WARPS][n_nodes]
+    int* cursor = sm_i + WARPS * n_nodes;  // [n_nodes]
+    const int r = blockIdx.x;
+    const int w = warp_id(), lane = lane_id();
+    const int64_t start = range_list[2 * r], end = range_list[2 * r + 1];
+    for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32) cursor[n] = 0;
+    constexpr int TILE = WARPS * 32 * GRP_ROUNDS;
+    for (int dir = 0; dir <= doubled; ++dir) {
+        for (int64_t tile = start; tile < end; tile += TILE) {
+            for (int i = threadIdx.x; i < WARPS * n_nodes; i += WARPS * 32) wh[i] = 0;
+            __syncthreads();
+            const int64_t wbase = tile + int64_t(w) * 32 * GRP_ROUNDS;
+            for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
+                const int64_t e = wbase + rd * 32 + lane;
+                int node = 0, oth = 0;
+                const bool valid = e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, oth);
+                const unsigned act = __ballot_sync(FULL, valid);
+                if (valid) {
+                    const unsigned peers = __match_any_sync(act, node);
+                    if ((__ffs(peers) - 1) == lane) wh[w * n_nodes + node] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32) {
+                int run = cursor[n];
+#pragma unroll
+                for (int ww = 0; ww < WARPS; ++ww) {
+                    const int c = wh[ww * n_nodes + n];
+                    wh[ww * n_nodes + n] = run;
+                    run += c;
+                }
+                cursor[n] = run;
+            }
+            __syncthreads();
+            for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
+                const int64_t e = wbase + rd * 32 + lane;
+                int node = 0, oth = 0;
+                const bool valid = e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, oth);
+                const unsigned act = __ballot_sync(FULL, valid);
+                unsigned peers = 0;
+                int pos = 0;
+                if (valid) {
+                    peers = __match_any_sync(act, node);
+                    pos = seg_start[int64_t(node) * n_rel + r] + wh[w * n_nodes + node] + __popc(peers & ((1u << lane) - 1u));
+                }
+                __syncwarp();
+                if (valid && (__ffs(peers) - 1) == lane) wh[w * n_nodes + node] += __popc(peers);
+                __syncwarp();
+                if (valid) {
+                    eid[pos] = int(dir ? E + e : e);
+                    other_out[pos] = oth;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// dense key space -> compact segment table
+__global__ void k_grp_segments(const int* __restrict__ cnt, const int* __restrict__ seg_start,
+                               const int* __restrict__ seg_index, int64_t n_keys, int n_rel, int* __restrict__ seg_ptr,
+                               int* __restrict__ seg_node, int* __restrict__ seg_rel, int* __restrict__ counts) {
+    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q > n_keys) return;
+    if (q == n_keys) {
+        const int S = seg_index[n_keys];
+        counts[TIPB_CSR_COUNT_SEGMENTS] = S;
+        counts[TIPB_CSR_COUNT_VALID] = seg_start[n_keys];
+        seg_ptr[S] = seg_start[n_keys];
+        return;
+    }
+    if (cnt[q] > 0) {
+        const int s = seg_index[q];
+        seg_ptr[s] = seg_start[q];
+        seg_node[s] = int(q / n_rel);
+        seg_rel[s] = int(q % n_rel);
+    }
+}
+
+__global__ void k_flag_positive(const int* __restrict__ cnt, int64_t n, int* __restrict__ flags) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = cnt[i] > 0 ? 1 : 0;
+}
+
+static int grp_warps(int64_t n_nodes) {
+    // shared memory: (WARPS + 1) * n_nodes ints
+    if (9 * n_nodes * 4 <= 96 * 1024) return 8;
+    if (5 * n_nodes * 4 <= 160 * 1024) return 4;
+    if (3 * n_nodes * 4 <= 200 * 1024) return 2;
+    return 0;
+}
+
+static bool use_grouped(const int64_t* edge_type, const int64_t* range_list, int64_t entries, int64_t n_nodes,
+                        int64_t n_rel) {
+    return range_list && !edge_type && entries > 0 && n_rel > 1 && n_rel <= 65535 && grp_warps(n_nodes) > 0 &&
+           n_nodes * n_rel <= 4 * entries + (int64_t(1) << 20);
+}
+
 size_t csr_build_ws_bytes(int64_t entries, int64_t n_nodes, int64_t n_rel) {
     CsrLayout L = make_layout(entries, n_nodes, n_rel);
     int64_t m = entries > L.seg_cap ? entries : L.seg_cap;
-    size_t arrays = 5 * (((m + 1) * 4 + 255) & ~size_t(255));
-    return arrays + sort_ws_bytes(m) + scan_ws_bytes(m + 1) + 1024;
+    const int64_t dense = n_nodes * n_rel;
+    if (dense <= 4 * entries + (int64_t(1) << 20) && dense > m) m = dense;  // grouped path scans the dense key space
+    size_t arrays = 5 * (((m + 2) * 4 + 255) & ~size_t(255));
+    return arrays + sort_ws_bytes(m) + scan_ws_bytes(m + 2) + 1024;
 }
 
 int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list, int64_t E,
@@ -225,19 +382,47 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
     const uint32_t sentinel = uint32_t(n_nodes * n_rel);
     const int T = 256;
     int64_t m = entries > v.seg_cap ? entries : v.seg_cap;
+    const int64_t dense = n_nodes * n_rel;
+    if (dense <= 4 * entries + (int64_t(1) << 20) && dense > m) m = dense;  // same rule as csr_build_ws_bytes
     Carver c(ws);
-    uint32_t* k0 = c.take<uint32_t>(m + 1);
-    uint32_t* v0 = c.take<uint32_t>(m + 1);
-    uint32_t* k1 = c.take<uint32_t>(m + 1);
-    uint32_t* v1 = c.take<uint32_t>(m + 1);
-    int* flags = c.take<int>(m + 1);
+    uint32_t* k0 = c.take<uint32_t>(m + 2);
+    uint32_t* v0 = c.take<uint32_t>(m + 2);
+    uint32_t* k1 = c.take<uint32_t>(m + 2);
+    uint32_t* v1 = c.take<uint32_t>(m + 2);
+    int* flags = c.take<int>(m + 2);
     void* sort_ws = c.take<char>(sort_ws_bytes(m));
-    void* scan_ws = c.take<char>(scan_ws_bytes(m + 1));
+    void* scan_ws = c.take<char>(scan_ws_bytes(m + 2));
 
     TIPB_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, 16 * sizeof(int), s));
     TIPB_CHECK_CUDA(cudaMemsetAsync(v.seg_ptr, 0, (v.seg_cap + 1) * sizeof(int), s));
     int rc;
-    if (entries > 0) {
+    if (use_grouped(edge_type, range_list, entries, n_nodes, n_rel)) {
+        const int64_t n_keys = n_nodes * n_rel;
+        int* cnt = reinterpret_cast<int*>(k0);
+        int* seg_start = reinterpret_cast<int*>(v0);
+        int* seg_index = flags;
+        TIPB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (n_keys + 1) * sizeof(int), s));
+        k_grp_check_ranges<<<(unsigned)ceil_div(n_rel, T), T, 0, s>>>(range_list, (int)n_rel, E, v.counts);
+        k_grp_count<<<dim3(8, (unsigned)n_rel), 256, 0, s>>>(edge_index, range_list, E, doubled, (int)n_nodes, (int)n_other,
+                                                            (int)n_rel, by_src, drop_loops, cnt, v.counts);
+        if ((rc = exclusive_scan_i32(cnt, seg_start, n_keys, scan_ws, s))) return rc;
+        k_flag_positive<<<(unsigned)ceil_div(n_keys, T), T, 0, s>>>(cnt, n_keys, seg_index);
+        if ((rc = exclusive_scan_i32(seg_index, seg_index, n_keys, scan_ws, s))) return rc;
+        k_grp_segments<<<(unsigned)ceil_div(n_keys + 1, T), T, 0, s>>>(cnt, seg_start, seg_index, n_keys, (int)n_rel,
+                                                                       v.seg_ptr, v.seg_node, v.seg_rel, v.counts);
+        const int warps = grp_warps(n_nodes);
+        const size_t smem = size_t(warps + 1) * n_nodes * sizeof(int);
+#define GRP_SCATTER(WV)                                                                                             \
+        {                                                                                                           \
+            auto kern = k_grp_scatter<WV>;                                                                          \
+            if ((rc = ensure_dyn_smem((const void*)kern, smem))) return rc;                                         \
+            kern<<<(unsigned)n_rel, WV * 32, smem, s>>>(edge_index, range_list, E, doubled, (int)n_nodes,           \
+                                                        (int)n_other, (int)n_rel, by_src, drop_loops, seg_start,    \
+                                                        v.eid, v.other);                                            \
+        }
+        if (warps == 8) GRP_SCATTER(8) else if (warps == 4) GRP_SCATTER(4) else GRP_SCATTER(2)
+#undef GRP_SCATTER
+    } else if (entries > 0) {
         unsigned g = (unsigned)ceil_div(entries, T);
         k_csr_keys<<<g, T, 0, s>>>(edge_index, edge_type, range_list, E, entries, (int)n_nodes, (int)n_other,
                                     (int)n_rel, by_src, drop_loops, k0, v0, v.counts);

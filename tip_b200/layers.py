@@ -363,14 +363,20 @@ class TIP(nn.Module):
 
     def forward(self, check_status=True):
         d = self.data
-        self.embeddings = self._encode()
         if self._neg_index is None:
             self._neg_index = torch.empty_like(d.dd_train_idx)
             self._neg_plan = ops.TypedCSR(d.dd_train_idx.shape[1], d.n_drug, d.n_dd_et, self.device, by_src=False,
                                           doubled=True)
-        neg_index = typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range, check_status=check_status,
-                                            out=self._neg_index)
-        self._neg_plan.build(neg_index, range_list=d.dd_train_range)
+            self._side = torch.cuda.Stream(device=self.device)
+        # the negatives do not depend on the encoder: sample and index them on a side stream meanwhile
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            neg_index = typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range,
+                                                check_status=check_status, out=self._neg_index)
+            self._neg_plan.build(neg_index, range_list=d.dd_train_range)
+        self.embeddings = self._encode()
+        cur.wait_stream(self._side)
         pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False,
                                    doubled=True)
         # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient

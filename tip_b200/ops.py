@@ -18,9 +18,9 @@ _workspaces = {}
 
 
 def workspace(nbytes, device, tag="ws"):
-    """A reusable scratch buffer (grown geometrically).  All library calls are ordered on the
-    current stream, so one buffer per (device, tag) is enough."""
-    key = (device.index, tag)
+    """A reusable scratch buffer (grown geometrically).  Library calls are ordered on the current
+    stream, so one buffer per (device, tag, stream) is enough and never shared across streams."""
+    key = (device.index, tag, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
