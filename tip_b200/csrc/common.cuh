@@ -78,11 +78,29 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
+// float4 arithmetic on Blackwell's packed FP32 pipe: FADD2 / FFMA2 / FMUL2 process two fp32 lanes per
+// instruction (sm_100 only), halving the issue slots of the gather-accumulate loops, which are issue bound.
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
-    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 c) {
-    return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+    const float2 ss = make_float2(s, s);
+    const float2 lo = __ffma2_rn(ss, make_float2(a.x, a.y), make_float2(c.x, c.y));
+    const float2 hi = __ffma2_rn(ss, make_float2(a.z, a.w), make_float2(c.z, c.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) {
+    const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// a.b over four lanes: two packed ops + one scalar add
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) {
+    float2 p = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    p = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), p);
+    return p.x + p.y;
 }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 

@@ -25,6 +25,8 @@ constexpr float TIP_EPS = 1e-13f;  // reference src/layers.py:15
 enum { DEC_MODE_POS = 0, DEC_MODE_NEG = 1, DEC_MODE_GRAD = 2 };
 
 __device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+// SFU versions for the fused loss kernel (MUFU.EX2 / MUFU.RCP / MUFU.LG2): a few ulp, far inside rtol 1e-4
+__device__ __forceinline__ float sigmoidf_fast(float v) { return __frcp_rn(1.0f + __expf(-v)); }
 
 // ------------------------------------------------------------------------------------------------
 // plain forward in the caller's edge order (the module's public forward)
@@ -82,7 +84,7 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
         const int node = seg_node[s], rel = seg_rel[s];
         const float4 zn = s_z[node * LPR + l];
         const float4 wr = w[rel * LPR + l];
-        const float4 u = make_float4(zn.x * wr.x, zn.y * wr.y, zn.z * wr.z, zn.w * wr.w);
+        const float4 u = f4_mul(zn, wr);
         float4 acc = f4_zero();
 
         for (int base = beg; base < end; base += 32) {
@@ -102,7 +104,7 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
                 const int k = r * G + g;
                 const int j = __shfl_sync(FULL, idx, k);
                 zj[r] = s_z[j * LPR + l];
-                float p = (u.x * zj[r].x + u.y * zj[r].y) + (u.z * zj[r].z + u.w * zj[r].w);
+                float p = f4_dot(u, zj[r]);
 #pragma unroll
                 for (int o = LPR >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
                 // entry k's value sits on every lane of group g; lane k fetches it from lane (k % G) * LPR
@@ -114,20 +116,20 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
             if (lane < cnt) {
                 if (MODE == DEC_MODE_GRAD) {
                     if (apply_sigmoid) {
-                        const float sg = sigmoidf_ref(vmine);
+                        const float sg = sigmoidf_fast(vmine);
                         gmine = go * sg * (1.f - sg);
                     } else {
                         gmine = go;
                     }
                 } else {
-                    const float sg = sigmoidf_ref(vmine);
+                    const float sg = sigmoidf_fast(vmine);
                     if (MODE == DEC_MODE_POS) {
-                        loss -= logf(sg + TIP_EPS);
-                        gmine = -(sg * (1.f - sg)) / (sg + TIP_EPS) * inv_count;
+                        loss -= __logf(sg + TIP_EPS);
+                        gmine = -__fdividef(sg * (1.f - sg), sg + TIP_EPS) * inv_count;
                     } else {
                         const float om = 1.f - sg;
-                        loss -= logf(om + TIP_EPS);
-                        gmine = (sg * om) / (om + TIP_EPS) * inv_count;
+                        loss -= __logf(om + TIP_EPS);
+                        gmine = __fdividef(sg * om, om + TIP_EPS) * inv_count;
                     }
                 }
             }
@@ -146,8 +148,8 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
             acc.w += __shfl_xor_sync(FULL, acc.w, o);
         }
         if (g == 0) {
-            acc_seg[int64_t(s) * LPR + l] = make_float4(acc.x * wr.x, acc.y * wr.y, acc.z * wr.z, acc.w * wr.w);
-            zacc_seg[int64_t(s) * LPR + l] = make_float4(acc.x * zn.x, acc.y * zn.y, acc.z * zn.z, acc.w * zn.w);
+            acc_seg[int64_t(s) * LPR + l] = f4_mul(acc, wr);
+            zacc_seg[int64_t(s) * LPR + l] = f4_mul(acc, zn);
         }
     }
     if (MODE != DEC_MODE_GRAD) {
@@ -265,10 +267,10 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
 #undef RUN
     k_decoder_node_reduce<<<(unsigned)v.n_nodes, 128, 0, s>>>(v.node_ptr, acc_seg, dim, accumulate, d_z);
     if (accumulate) {
-        k_rel_reduce<<<(unsigned)v.n_rel, 128, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, dw_tmp);
+        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, dw_tmp);
         k_add_inplace<<<(unsigned)ceil_div(v.n_rel * dim, 256), 256, 0, s>>>(d_w, dw_tmp, v.n_rel * dim);
     } else {
-        k_rel_reduce<<<(unsigned)v.n_rel, 128, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, d_w);
+        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, d_w);
     }
     if (mode != DEC_MODE_GRAD)
         k_loss_reduce<<<1, 1024, 0, s>>>(loss_part, n_warps, 0.5f * inv_count, accumulate, loss_out);

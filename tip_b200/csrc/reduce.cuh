@@ -4,28 +4,43 @@
 
 namespace tipb {
 
-// per-relation reduction of per-segment rows:  dst[r, :] = sum_{s in rel_seg[r]} src[s, :]   (row width w)
-static __global__ void __launch_bounds__(128)
+constexpr int REL_REDUCE_THREADS = 256;
+
+// dst[r, :] = scale * sum_{s in rel_seg[rel_seg_ptr[r] .. rel_seg_ptr[r+1])} src[s, :]      (row width w)
+// One CTA per relation; warp k takes rows k, k+8, ... with four rows in flight; the eight warp partials are
+// added in a fixed order, so the result does not depend on scheduling.
+static __global__ void __launch_bounds__(REL_REDUCE_THREADS)
 k_rel_reduce(const int* __restrict__ rel_seg_ptr, const int* __restrict__ rel_seg, const float* __restrict__ src,
              int w, float scale, float* __restrict__ dst) {
-    __shared__ float part[4][128];
+    constexpr int NW = REL_REDUCE_THREADS / 32;
+    __shared__ float part[NW][32];
     const int r = blockIdx.x;
     const int beg = rel_seg_ptr[r], end = rel_seg_ptr[r + 1];
     const int wid = warp_id(), lane = lane_id();
     for (int c0 = 0; c0 < w; c0 += 32) {
         const int col = c0 + lane;
-        float a0 = 0.f, a1 = 0.f;
+        const bool ok = col < w;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int p = beg + wid;
-        for (; p + 4 < end; p += 8) {
-            int s0 = rel_seg[p], s1 = rel_seg[p + 4];
-            if (col < w) { a0 += src[int64_t(s0) * w + col]; a1 += src[int64_t(s1) * w + col]; }
+        for (; p + 3 * NW < end; p += 4 * NW) {
+            const int s0 = rel_seg[p], s1 = rel_seg[p + NW], s2 = rel_seg[p + 2 * NW], s3 = rel_seg[p + 3 * NW];
+            if (ok) {
+                a0 += src[int64_t(s0) * w + col];
+                a1 += src[int64_t(s1) * w + col];
+                a2 += src[int64_t(s2) * w + col];
+                a3 += src[int64_t(s3) * w + col];
+            }
         }
-        for (; p < end; p += 4)
-            if (col < w) a0 += src[int64_t(rel_seg[p]) * w + col];
-        part[wid][lane] = a0 + a1;
+        for (; p < end; p += NW)
+            if (ok) a0 += src[int64_t(rel_seg[p]) * w + col];
+        part[wid][lane] = (a0 + a1) + (a2 + a3);
         __syncthreads();
-        if (wid == 0 && col < w)
-            dst[int64_t(r) * w + col] = scale * (((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane]);
+        if (wid == 0 && ok) {
+            float t = part[0][lane];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) t += part[k][lane];
+            dst[int64_t(r) * w + col] = scale * t;
+        }
         __syncthreads();
     }
 }

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "seg_aggregate.cuh"
 #include "reduce.cuh"
+#include "rgcn_tiled.cuh"
 
 namespace tipb {
 
@@ -282,7 +283,67 @@ __global__ void k_sum_slices(const float* __restrict__ partial, int64_t n, int k
     out[i] = s;
 }
 
+// shared-memory tiled variant: CTA tile 64 (M) x N, K chunk 32; each thread owns RPT rows x 4 columns
+// (RPT = N / 16), reads one float4 of B and RPT scalars of A per k and issues RPT FFMA2 pairs.
+constexpr int ATBT_ROWS = 64, ATBT_KC = 32;
+template <int N>
+__global__ void __launch_bounds__(256)
+k_atb_tiled(const float* __restrict__ A, const float* __restrict__ Bm, int K, int M, int k_slices,
+            float* __restrict__ partial) {
+    constexpr int RPT = N / 16, CG = N / 4;
+    __shared__ float As[ATBT_KC][ATBT_ROWS];
+    __shared__ float4 Bs[ATBT_KC][CG];
+    const int tid = threadIdx.x;
+    const int c4 = tid % CG, rg = tid / CG;
+    const int row0 = blockIdx.x * ATBT_ROWS;
+    const int ks = blockIdx.y;
+    const int kc = (K + k_slices - 1) / k_slices;
+    const int kb = ks * kc, ke = min(K, kb + kc);
+    float4 acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i] = f4_zero();
+    for (int k0 = kb; k0 < ke; k0 += ATBT_KC) {
+        const int kn = min(ATBT_KC, ke - k0);
+        for (int i = tid; i < ATBT_KC * ATBT_ROWS; i += 256) {
+            const int kk = i / ATBT_ROWS, r = i % ATBT_ROWS;
+            As[kk][r] = (kk < kn && row0 + r < M) ? A[int64_t(k0 + kk) * M + row0 + r] : 0.f;
+        }
+        for (int i = tid; i < ATBT_KC * CG; i += 256) {
+            const int kk = i / CG, c = i % CG;
+            Bs[kk][c] = kk < kn ? reinterpret_cast<const float4*>(Bm)[int64_t(k0 + kk) * CG + c] : f4_zero();
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < ATBT_KC; ++kk) {
+            const float4 b = Bs[kk][c4];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) acc[i] = f4_fma(As[kk][rg * RPT + i], b, acc[i]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int row = row0 + rg * RPT + i;
+        if (row < M) reinterpret_cast<float4*>(partial)[(int64_t(ks) * M + row) * CG + c4] = acc[i];
+    }
+}
+
 int atb_launch(const float* A, const float* Bm, int K, int M, int N, float* out, float* partial_ws, cudaStream_t s) {
+    if (N == 16 || N == 32 || N == 64 || N == 128) {
+        const int tiles = (int)ceil_div(M, ATBT_ROWS);
+        int k_slices = (int)ceil_div(2 * sm_count(), tiles);
+        if (k_slices > 32) k_slices = 32;
+        const int max_slices = (int)ceil_div(K > 0 ? K : 1, ATBT_KC);
+        if (k_slices > max_slices) k_slices = max_slices;
+        const dim3 grid(tiles, k_slices);
+        if (N == 16) k_atb_tiled<16><<<grid, 256, 0, s>>>(A, Bm, K, M, k_slices, partial_ws);
+        else if (N == 32) k_atb_tiled<32><<<grid, 256, 0, s>>>(A, Bm, K, M, k_slices, partial_ws);
+        else if (N == 64) k_atb_tiled<64><<<grid, 256, 0, s>>>(A, Bm, K, M, k_slices, partial_ws);
+        else k_atb_tiled<128><<<grid, 256, 0, s>>>(A, Bm, K, M, k_slices, partial_ws);
+        k_sum_slices<<<(unsigned)ceil_div(int64_t(M) * N, 256), 256, 0, s>>>(partial_ws, int64_t(M) * N, k_slices, out);
+        TIPB_CHECK_LAUNCH("atb_tiled");
+        return TIPB_OK;
+    }
     // enough CTAs to cover the machine, but never more slices than rows of K
     int tiles = (int)ceil_div(M, ATB_ROWS);
     int k_slices = (int)ceil_div(2 * sm_count(), tiles);
@@ -369,9 +430,34 @@ int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, i
     float* H = c.take<float>(size_t(v.seg_cap) * f_in);
     if ((rc = seg_aggregate_launch(v, x, nullptr, nullptr, (int)n_nodes, f_in, H, s))) return rc;
 
+    // register-tiled kernel for the common shapes
+#define TILED_FWD(TFV, NBQV)                                                                                       \
+    {                                                                                                              \
+        auto kern = k_rgcn_node_fwd_tiled<TFV, NBQV>;                                                              \
+        const size_t sm = node_fwd_tiled_smem<TFV, NBQV>();                                                        \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, TILED_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, v.inv_deg, (const float4*)H,      \
+                                                          (const float4*)att, basis, root, bias, x, f_out, relu_out, \
+                                                          out, (float4*)g_saved);                                  \
+        TIPB_CHECK_LAUNCH("rgcn_node_fwd_tiled");                                                                  \
+        return TIPB_OK;                                                                                            \
+    }
+    if (f_out <= TILED_THREADS) {
+        if (n_bases == 32) {
+            if (f_in == 64) TILED_FWD(16, 8)
+            if (f_in == 32) TILED_FWD(8, 8)
+            if (f_in == 16) TILED_FWD(4, 8)
+        } else if (n_bases == 16) {
+            if (f_in == 64) TILED_FWD(16, 4)
+            if (f_in == 32) TILED_FWD(8, 4)
+            if (f_in == 16) TILED_FWD(4, 4)
+        }
+    }
+#undef TILED_FWD
+
     const int nb = pick_nb(n_bases, NODE_THREADS / (f_in / 4));
     const size_t smem = node_fwd_smem(f_in, n_bases);
-#define LAUNCH_FWD(NBV)                                                                                            \
+#define LAUNCH_FWD(NBV)                                                                                           \
     {                                                                                                              \
         auto kern = k_rgcn_node_fwd<NBV>;                                                                          \
         if ((rc = ensure_dyn_smem((const void*)kern, smem))) return rc; \
@@ -424,14 +510,33 @@ int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, i
                                                            (const float4*)basis, (const float4*)root, x, geff, f_in, \
                                                            f_out, n_bases, datt_seg, d_x);                         \
     }
-    switch (nb) {
-        case 1: LAUNCH_BWD(1) break;
-        case 2: LAUNCH_BWD(2) break;
-        case 4: LAUNCH_BWD(4) break;
-        default: LAUNCH_BWD(8) break;
+    bool tiled = false;
+#define TILED_BWD(TFV, NBQV)                                                                                       \
+    {                                                                                                              \
+        auto kern = k_rgcn_node_bwd_tiled<TFV, NBQV>;                                                              \
+        const size_t sm = node_bwd_tiled_smem<TFV, NBQV>(f_in);                                                    \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, TILED_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, (const float4*)T, (const float4*)att, \
+                                                          (const float4*)basis, (const float4*)root, x, geff, f_in, \
+                                                          datt_seg, d_x);                                          \
+        tiled = true;                                                                                              \
+    }
+    if (n_bases == 32) {
+        if (f_out == 64) TILED_BWD(16, 8) else if (f_out == 32) TILED_BWD(8, 8) else if (f_out == 16) TILED_BWD(4, 8)
+    } else if (n_bases == 16) {
+        if (f_out == 64) TILED_BWD(16, 4) else if (f_out == 32) TILED_BWD(8, 4) else if (f_out == 16) TILED_BWD(4, 4)
+    }
+#undef TILED_BWD
+    if (!tiled) {
+        switch (nb) {
+            case 1: LAUNCH_BWD(1) break;
+            case 2: LAUNCH_BWD(2) break;
+            case 4: LAUNCH_BWD(4) break;
+            default: LAUNCH_BWD(8) break;
+        }
     }
 #undef LAUNCH_BWD
-    k_rel_reduce<<<(unsigned)n_rel, 128, 0, s>>>(v.rel_seg_ptr, v.rel_seg, datt_seg, n_bases, 1.0f, d_att);
+    k_rel_reduce<<<(unsigned)n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, datt_seg, n_bases, 1.0f, d_att);
     if ((rc = atb_launch(g_saved, ghat, (int)n_nodes, m_basis, f_out, d_basis, partial, s))) return rc;
     if ((rc = atb_launch(x, geff, (int)n_nodes, f_in, f_out, d_root, partial, s))) return rc;
     TIPB_CHECK_LAUNCH("rgcn_bwd");
