@@ -69,7 +69,8 @@ enum {
 enum {
     TIPB_CSR_COUNT_SEGMENTS = 0, /* S: number of non-empty segments */
     TIPB_CSR_COUNT_VALID = 1,    /* entries kept (self loops / out-of-range entries are dropped) */
-    TIPB_CSR_COUNT_STATUS = 2    /* bit0: an index was out of range */
+    TIPB_CSR_COUNT_STATUS = 2,   /* bit0: an index was out of range; bit1: range_list is not cumulative */
+    TIPB_CSR_COUNT_REL_MAJOR = 3 /* 1: segments are ordered (relation, node) instead of (node, relation) */
 };
 size_t tipb_typed_csr_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel);
 size_t tipb_typed_csr_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_rel);
@@ -77,11 +78,16 @@ int tipb_typed_csr_layout(int64_t n_entries, int64_t n_nodes, int64_t n_rel,
                           int64_t* offsets_bytes /* [TIPB_CSR_NFIELDS] */, int64_t* seg_capacity);
 /* edge_type may be NULL when range_list ([n_rel,2], cumulative) is given, and both may be NULL when
  * n_rel == 1.  by_src=0 groups by edge_index[1] (message target), 1 by edge_index[0].
- * doubled=1 lists each edge in both directions (n_entries = 2*n_edges). */
+ * doubled=1 lists each edge in both directions (n_entries = 2*n_edges).
+ * rel_major=0: segments ordered (node, relation): NODE_PTR gives each node's segment range directly and
+ *              REL_SEG_PTR/REL_SEG list the segment ids relation by relation (what the R-GCN kernels need);
+ * rel_major=1: segments ordered (relation, node): REL_SEG_PTR gives each relation's segment range directly and
+ *              NODE_PTR indexes REL_SEG, which then lists the segment ids node by node (decoder plans: every
+ *              relation's entries stay together, so building the plan of a fresh negative sample is local). */
 int tipb_typed_csr_build(const int64_t* edge_index /* [2,n_edges] */, const int64_t* edge_type,
                          const int64_t* range_list, int64_t n_edges, int64_t n_nodes, int64_t n_other,
-                         int64_t n_rel, int by_src, int doubled, int drop_self_loops, void* plan, size_t plan_bytes,
-                         void* ws, size_t ws_bytes, void* stream);
+                         int64_t n_rel, int by_src, int doubled, int drop_self_loops, int rel_major, void* plan,
+                         size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- R-GCN with basis decomposition
  * Replaces MyRGCNConv.forward / MyRGCNConv2.forward (src/layers.py:76-94, 157-188) and their
@@ -160,7 +166,7 @@ int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int
  *                 [0,624) = the key block itself, then n_new further words (tipb_mt19937_generate).
  *                 It depends on the state only, so the host may produce it ahead of time.
  *   member        per-relation bitmaps of the positive pairs (+ their popcounts) from tipb_neg_bitmap_build.
- *   table         per-relation brackets of the stream offsets (6 int64 per relation: lo, W, L, win_off, f_off, k)
+ *   table         per-relation brackets of the stream offsets (7 int64 per relation: lo, W, L, win_off, f_off, k, pred)
  *                 built ON THE HOST from host copies of range_list and the popcounts (tipb_neg_table_build,
  *                 no CUDA call); totals[0..3] = sum_L, sum_W, highest accepted index a window may touch,
  *                 expected accepted values consumed.
@@ -175,7 +181,7 @@ int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_li
                           int64_t n_nodes, int64_t n_rel, uint32_t* member, int32_t* popcount /* [n_rel] */,
                           void* stream);
 int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount_host, int64_t n_rel,
-                         int64_t n_nodes, double z_sigma, int64_t* table_host /* [n_rel*6] */,
+                         int64_t n_nodes, double z_sigma, int64_t* table_host /* [n_rel*7] */,
                          int64_t* totals_host /* [4] */);
 size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n_words, int64_t sum_l,
                                        int64_t sum_w);

@@ -46,14 +46,26 @@ def process_edges(rng, raw_edge_list, p=0.9):
     return tuple(res)
 
 
-def typed_csr(edge_index, edge_type, n_nodes, n_rel, by="dst"):
+def typed_csr(edge_index, edge_type, n_nodes, n_rel, by="dst", rel_major=False):
     """Index structures of the CUDA path (tip_b200/csrc/typed_csr.cu), by definition:
-    STABLE sort of the edges by (node, relation) -- ties keep their input order --
-    where node is the target (by='dst') or the source (by='src') endpoint.
+    STABLE sort of the edges by (node, relation) -- or (relation, node) when rel_major --
+    ties keep their input order; node is the target (by='dst') or the source (by='src') endpoint.
 
-    returns dict(eid, other, seg_ptr, seg_node, seg_rel, node_ptr, deg)."""
+    returns dict(eid, other, seg_ptr, seg_node, seg_rel, node_ptr, deg); for rel_major plans
+    node_ptr is not defined here (the CUDA plan lists a node's segments through rel_seg)."""
     a, b = (1, 0) if by == "dst" else (0, 1)
     node, other = edge_index[a].astype(np.int64), edge_index[b].astype(np.int64)
+    if rel_major:
+        order = np.lexsort((node, edge_type))
+        key = edge_type[order] * n_nodes + node[order]
+        first = np.ones(order.size, dtype=bool)
+        first[1:] = key[1:] != key[:-1]
+        seg_start = np.nonzero(first)[0]
+        seg_key = key[seg_start]
+        return dict(eid=order.astype(np.int32), other=other[order].astype(np.int32),
+                    seg_ptr=np.concatenate([seg_start, [order.size]]).astype(np.int32),
+                    seg_node=(seg_key % n_nodes).astype(np.int32), seg_rel=(seg_key // n_nodes).astype(np.int32),
+                    deg=np.bincount(node, minlength=n_nodes).astype(np.int32))
     order = np.lexsort((edge_type, node))                  # last key is primary; stable
     key = node[order] * n_rel + edge_type[order]
     first = np.ones(order.size, dtype=bool)

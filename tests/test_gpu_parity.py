@@ -91,6 +91,52 @@ def _check_plan(plan, ei, et, n, r, by, doubled=False, drop_loops=False):
     assert np.array_equal(rp, np.searchsorted(ref["seg_rel"][rs], np.arange(r + 1)).astype(np.int32))
 
 
+def _check_rel_major_plan(plan, ei, et, n, r, doubled):
+    """relation-major plans: segments ordered (relation, node); a node's segments through the listing"""
+    from oracle import layout_oracle as lo
+    ei, et = np.asarray(ei), np.asarray(et)
+    if doubled:
+        ei = np.concatenate([ei, ei[::-1]], axis=1)
+        et = np.concatenate([et, et])
+    ref = lo.typed_csr(ei, et, n, r, by="dst", rel_major=True)
+    cnt = plan.field("counts").cpu().numpy()
+    S = int(cnt[0])
+    assert S == len(ref["seg_node"]) and int(cnt[1]) == ei.shape[1] and int(cnt[2]) == 0 and int(cnt[3]) == 1
+    assert np.array_equal(plan.field("eid").cpu().numpy(), ref["eid"])
+    assert np.array_equal(plan.field("other").cpu().numpy(), ref["other"])
+    assert np.array_equal(plan.field("seg_ptr").cpu().numpy()[:S + 1], ref["seg_ptr"])
+    assert np.array_equal(plan.field("seg_node").cpu().numpy()[:S], ref["seg_node"])
+    assert np.array_equal(plan.field("seg_rel").cpu().numpy()[:S], ref["seg_rel"])
+    assert np.array_equal(plan.field("rel_seg_ptr").cpu().numpy(), np.searchsorted(ref["seg_rel"], np.arange(r + 1)))
+    listing = plan.field("rel_seg").cpu().numpy()[:S]
+    assert np.array_equal(listing, np.argsort(ref["seg_node"], kind="stable").astype(np.int32))
+    assert np.array_equal(plan.field("node_ptr").cpu().numpy(),
+                          np.searchsorted(ref["seg_node"][listing], np.arange(n + 1)).astype(np.int32))
+    assert np.array_equal(plan.field("deg").cpu().numpy(), ref["deg"])
+
+
+def test_typed_csr_relation_major(golden_layers):
+    from tip_b200 import ops
+    d = dev()
+    g = golden_layers
+    ei, et, rl = g["data/dd_train_idx"], g["data/dd_train_et"], g["data/dd_train_range"]
+    n, r = int(g["data/n_drug"]), int(g["data/n_dd_et"])
+    for doubled in (False, True):
+        grouped = ops.TypedCSR(ei.shape[1], n, r, d, doubled=doubled, rel_major=True).build(T(ei, d), range_list=T(rl, d))
+        _check_rel_major_plan(grouped, ei, et, n, r, doubled)
+        generic = ops.TypedCSR(ei.shape[1], n, r, d, doubled=doubled, rel_major=True).build(T(ei, d), edge_type=T(et, d))
+        assert torch.equal(grouped.buf, generic.buf)
+    rng = np.random.default_rng(9)
+    n, r, e = 645, 300, 400_000
+    sizes = rng.multinomial(e, rng.dirichlet(np.ones(r)))
+    ei = rng.integers(0, n, (2, e)).astype(np.int64)
+    et = np.repeat(np.arange(r), sizes).astype(np.int64)
+    ends = np.cumsum(sizes)
+    rl = np.stack([ends - sizes, ends], axis=1).astype(np.int64)
+    plan = ops.TypedCSR(e, n, r, d, doubled=True, rel_major=True).build(T(ei, d), range_list=T(rl, d))
+    _check_rel_major_plan(plan, ei, et, n, r, True)
+
+
 def test_typed_csr_bit_exact(golden_layers):
     from tip_b200 import ops
     d = dev()

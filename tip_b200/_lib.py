@@ -25,7 +25,7 @@ SIGNATURES = {
     "tipb_typed_csr_bytes": (_sz, [_i64, _i64, _i64]),
     "tipb_typed_csr_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "tipb_typed_csr_layout": (C.c_int, [_i64, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
-    "tipb_typed_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p, _sz, _p]),
+    "tipb_typed_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p, _sz, _p, _sz, _p]),
     "tipb_seg_aggregate": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i32, _p, _p]),
     "tipb_rgcn_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i32]),
     "tipb_rgcn_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),

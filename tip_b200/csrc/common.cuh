@@ -130,8 +130,8 @@ struct CsrView {
 CsrView csr_view(const void* plan, int64_t entries, int64_t n_nodes, int64_t n_rel);
 size_t csr_build_ws_bytes(int64_t entries, int64_t n_nodes, int64_t n_rel);
 int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list, int64_t E,
-              int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled, int drop_loops, void* plan,
-              void* ws, cudaStream_t s);
+              int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled, int drop_loops, int rel_major,
+              void* plan, void* ws, cudaStream_t s);
 
 // ---- internal cross-file entry points (all enqueue on `s`, never synchronise) ---------------
 size_t scan_ws_bytes(int64_t n);

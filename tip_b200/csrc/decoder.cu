@@ -160,15 +160,19 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
 
 // d_z[n, :] (+)= sum_{s in node n} wacc_seg[s, :]
 __global__ void __launch_bounds__(128)
-k_decoder_node_reduce(const int* __restrict__ node_ptr, const float* __restrict__ wacc_seg, int dim, int accumulate,
-                      float* __restrict__ d_z) {
+k_decoder_node_reduce(const int* __restrict__ node_ptr, const int* __restrict__ listing, const int* __restrict__ counts,
+                      const float* __restrict__ wacc_seg, int dim, int accumulate, float* __restrict__ d_z) {
     __shared__ float part[128];
     const int n = blockIdx.x;
     const int sb = node_ptr[n], se = node_ptr[n + 1];
+    const bool listed = counts[TIPB_CSR_COUNT_REL_MAJOR] != 0;  // relation-major plan: node_ptr indexes the listing
     const int per = 128 / dim;  // dim <= 128 and a power of two
     const int k = threadIdx.x % dim, sg = threadIdx.x / dim;
     float a = 0.f;
-    for (int s = sb + sg; s < se; s += per) a += wacc_seg[int64_t(s) * dim + k];
+    for (int i = sb + sg; i < se; i += per) {
+        const int s = listed ? listing[i] : i;
+        a += wacc_seg[int64_t(s) * dim + k];
+    }
     part[threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.x < dim) {
@@ -265,12 +269,12 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
     else if (mode == DEC_MODE_NEG) RUN(DEC_MODE_NEG)
     else RUN(DEC_MODE_GRAD)
 #undef RUN
-    k_decoder_node_reduce<<<(unsigned)v.n_nodes, 128, 0, s>>>(v.node_ptr, acc_seg, dim, accumulate, d_z);
+    k_decoder_node_reduce<<<(unsigned)v.n_nodes, 128, 0, s>>>(v.node_ptr, v.rel_seg, v.counts, acc_seg, dim, accumulate, d_z);
     if (accumulate) {
-        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, dw_tmp);
+        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, zacc_seg, dim, 0.5f, dw_tmp);
         k_add_inplace<<<(unsigned)ceil_div(v.n_rel * dim, 256), 256, 0, s>>>(d_w, dw_tmp, v.n_rel * dim);
     } else {
-        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, zacc_seg, dim, 0.5f, d_w);
+        k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, zacc_seg, dim, 0.5f, d_w);
     }
     if (mode != DEC_MODE_GRAD)
         k_loss_reduce<<<1, 1024, 0, s>>>(loss_part, n_warps, 0.5f * inv_count, accumulate, loss_out);

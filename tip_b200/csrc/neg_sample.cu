@@ -37,7 +37,7 @@ namespace tipb {
 constexpr int MT_N = 624, MT_M = 397, MT_LAG = MT_N - MT_M;  // 227
 constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MATRIX_A = 0x9908b0dfu;
 constexpr int RING = 2048;
-constexpr int TAB = 6;  // per-relation table row: lo, W, L, win_off, f_off, k
+constexpr int TAB = 7;  // per-relation table row: lo, W, L, win_off, f_off, k, pred (expected start offset)
 
 enum { NEG_STATUS_OUT_OF_WORDS = 1, NEG_STATUS_TOO_MANY_ROUNDS = 2, NEG_STATUS_BRACKET_MISS = 4 };
 
@@ -211,39 +211,56 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
     }
 }
 
-// one thread follows o_{r+1} = F_r[o_r - lo_r]
-__global__ void __launch_bounds__(256)
+// One warp follows o_{r+1} = F_r[o_r - lo_r].  Lane 0 does the dependent lookups; the other lanes pull the part of
+// F_{r+AHEAD} that the walk is going to need into L1: given o_r the start of relation r+AHEAD is known to within a
+// few hundred entries (pred[] = expected start offsets), far tighter than the bracket itself.
+constexpr int WALK_AHEAD = 16;
+__global__ void __launch_bounds__(32)
 k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n_rel, int* __restrict__ off,
              int* __restrict__ chain_out, int* __restrict__ status) {
-    extern __shared__ int s_tab[];  // per relation: lo, W, f_off (fits 32 bits), k
-    for (int i = threadIdx.x; i < n_rel; i += blockDim.x) {
+    extern __shared__ int s_tab[];  // per relation: lo, W, f_off (fits 32 bits), k, pred
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n_rel; i += 32) {
         const int64_t* tb = table + int64_t(i) * TAB;
-        s_tab[4 * i] = int(tb[0]);
-        s_tab[4 * i + 1] = int(tb[1]);
-        s_tab[4 * i + 2] = int(tb[4]);
-        s_tab[4 * i + 3] = int(tb[5]);
+        s_tab[5 * i] = int(tb[0]);
+        s_tab[5 * i + 1] = int(tb[1]);
+        s_tab[5 * i + 2] = int(tb[4]);
+        s_tab[5 * i + 3] = int(tb[5]);
+        s_tab[5 * i + 4] = int(tb[6]);
     }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+    __syncwarp();
     int o = 0;
     int r = 0;
+    int fail = 0;
     for (; r < n_rel; ++r) {
-        off[r] = o;
-        if (s_tab[4 * r + 3] == 0) continue;
-        const int x = o - s_tab[4 * r];
-        if (x < 0 || x >= s_tab[4 * r + 1]) {
-            atomicOr(status, NEG_STATUS_BRACKET_MISS);
-            break;
+        if (lane > 0) {
+            const int ra = r + WALK_AHEAD;
+            if (ra < n_rel) {
+                const int xp = o + (s_tab[5 * ra + 4] - s_tab[5 * r + 4]) - s_tab[5 * ra] + (lane - 16) * 32;
+                const int xc = min(max(xp, 0), s_tab[5 * ra + 1] - 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(F + s_tab[5 * ra + 2] + xc));
+            }
+        } else {
+            off[r] = o;
+            if (s_tab[5 * r + 3] != 0) {
+                const int x = o - s_tab[5 * r];
+                if (x < 0 || x >= s_tab[5 * r + 1]) {
+                    fail = NEG_STATUS_BRACKET_MISS;
+                } else {
+                    const int nxt = F[s_tab[5 * r + 2] + x];
+                    if (nxt < 0) fail = NEG_STATUS_OUT_OF_WORDS; else o = nxt;
+                }
+            }
         }
-        const int nxt = F[s_tab[4 * r + 2] + x];
-        if (nxt < 0) {
-            atomicOr(status, NEG_STATUS_OUT_OF_WORDS);
-            break;
-        }
-        o = nxt;
+        fail = __shfl_sync(FULL, fail, 0);
+        if (fail) break;
+        o = __shfl_sync(FULL, o, 0);
     }
-    for (int q = r; q < n_rel; ++q) off[q] = -1;  // relations that could not be placed (r == n_rel: none)
-    chain_out[0] = o;
+    if (lane == 0) {
+        if (fail) atomicOr(status, fail);
+        for (int q = r; q < n_rel; ++q) off[q] = -1;  // relations that could not be placed (r == n_rel: none)
+        chain_out[0] = o;
+    }
 }
 
 // rounds 0 and 1, one thread per draw
@@ -570,6 +587,7 @@ int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount
         const int64_t L = k == 0 ? 0 : W + k + int64_t(ceil(ek + z_sigma * sqrt(vk))) + slack;
         int64_t* tb = table_host + r * TAB;
         tb[0] = lo; tb[1] = W; tb[2] = L; tb[3] = sum_l; tb[4] = sum_w; tb[5] = k;
+        tb[6] = ksum + int64_t(llround(mean));
         sum_l += L;
         sum_w += W;
         if (lo + L > max_index) max_index = lo + L;
@@ -600,7 +618,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     TIPB_CHECK_ARG(exact_mode || table, "neg_sample: the fast path needs the bracket table");
     TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample: n_nodes must be in [2, 46340]");
     TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample: bad stream length");
-    TIPB_CHECK_ARG(n_rel > 0 && n_rel * 16 <= 200 * 1024, "neg_sample: n_rel out of range");
+    TIPB_CHECK_ARG(n_rel > 0 && n_rel * 20 <= 200 * 1024, "neg_sample: n_rel out of range");
     TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
                    "neg_sample: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
@@ -626,9 +644,9 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
     } else {
         k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
-        const size_t smem = size_t(n_rel) * 16;
+        const size_t smem = size_t(n_rel) * 20;
         if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
-        k_chain_walk<<<1, 256, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
+        k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
         if (n_edges > 0)
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,

@@ -10,12 +10,13 @@ constexpr int REL_REDUCE_THREADS = 256;
 // One CTA per relation; warp k takes rows k, k+8, ... with four rows in flight; the eight warp partials are
 // added in a fixed order, so the result does not depend on scheduling.
 static __global__ void __launch_bounds__(REL_REDUCE_THREADS)
-k_rel_reduce(const int* __restrict__ rel_seg_ptr, const int* __restrict__ rel_seg, const float* __restrict__ src,
-             int w, float scale, float* __restrict__ dst) {
+k_rel_reduce(const int* __restrict__ rel_seg_ptr, const int* __restrict__ rel_seg, const int* __restrict__ counts,
+             const float* __restrict__ src, int w, float scale, float* __restrict__ dst) {
     constexpr int NW = REL_REDUCE_THREADS / 32;
     __shared__ float part[NW][32];
     const int r = blockIdx.x;
     const int beg = rel_seg_ptr[r], end = rel_seg_ptr[r + 1];
+    const bool direct = counts[TIPB_CSR_COUNT_REL_MAJOR] != 0;  // relation-major plan: rows beg..end are the segments
     const int wid = warp_id(), lane = lane_id();
     for (int c0 = 0; c0 < w; c0 += 32) {
         const int col = c0 + lane;
@@ -23,7 +24,8 @@ k_rel_reduce(const int* __restrict__ rel_seg_ptr, const int* __restrict__ rel_se
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int p = beg + wid;
         for (; p + 3 * NW < end; p += 4 * NW) {
-            const int s0 = rel_seg[p], s1 = rel_seg[p + NW], s2 = rel_seg[p + 2 * NW], s3 = rel_seg[p + 3 * NW];
+            const int s0 = direct ? p : rel_seg[p], s1 = direct ? p + NW : rel_seg[p + NW];
+            const int s2 = direct ? p + 2 * NW : rel_seg[p + 2 * NW], s3 = direct ? p + 3 * NW : rel_seg[p + 3 * NW];
             if (ok) {
                 a0 += src[int64_t(s0) * w + col];
                 a1 += src[int64_t(s1) * w + col];
@@ -32,7 +34,7 @@ k_rel_reduce(const int* __restrict__ rel_seg_ptr, const int* __restrict__ rel_se
             }
         }
         for (; p < end; p += NW)
-            if (ok) a0 += src[int64_t(rel_seg[p]) * w + col];
+            if (ok) a0 += src[int64_t(direct ? p : rel_seg[p]) * w + col];
         part[wid][lane] = (a0 + a1) + (a2 + a3);
         __syncthreads();
         if (wid == 0 && ok) {

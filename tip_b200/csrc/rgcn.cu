@@ -536,7 +536,7 @@ int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, i
         }
     }
 #undef LAUNCH_BWD
-    k_rel_reduce<<<(unsigned)n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, datt_seg, n_bases, 1.0f, d_att);
+    k_rel_reduce<<<(unsigned)n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, datt_seg, n_bases, 1.0f, d_att);
     if ((rc = atb_launch(g_saved, ghat, (int)n_nodes, m_basis, f_out, d_basis, partial, s))) return rc;
     if ((rc = atb_launch(x, geff, (int)n_nodes, f_in, f_out, d_root, partial, s))) return rc;
     TIPB_CHECK_LAUNCH("rgcn_bwd");

@@ -76,12 +76,22 @@ CsrView csr_view(const void* plan, int64_t entries, int64_t n_nodes, int64_t n_r
     return v;
 }
 
+// segment key: node-major plans sort by (node, relation), relation-major plans by (relation, node)
+__host__ __device__ __forceinline__ int64_t seg_key(int64_t node, int64_t rel, int n_nodes, int n_rel, int rel_major) {
+    return rel_major ? rel * n_nodes + node : node * n_rel + rel;
+}
+__host__ __device__ __forceinline__ void seg_unkey(uint32_t key, int n_nodes, int n_rel, int rel_major, int& node,
+                                                   int& rel) {
+    if (rel_major) { rel = int(key / uint32_t(n_nodes)); node = int(key % uint32_t(n_nodes)); }
+    else { node = int(key / uint32_t(n_rel)); rel = int(key % uint32_t(n_rel)); }
+}
+
 // ------------------------------------------------------------------------------------------------
-// 1. keys: key = node * R + rel (sentinel N*R for dropped / out-of-range entries), val = entry id
+// 1. keys: key = seg_key(node, rel) (sentinel N*R for dropped / out-of-range entries), val = entry id
 __global__ void k_csr_keys(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
                            const int64_t* __restrict__ range_list, int64_t E, int64_t entries, int n_nodes,
-                           int n_other, int n_rel, int by_src, int drop_loops, uint32_t* __restrict__ keys,
-                           uint32_t* __restrict__ vals, int* __restrict__ counts) {
+                           int n_other, int n_rel, int by_src, int drop_loops, int rel_major,
+                           uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ counts) {
     int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= entries) return;
     int64_t e = p < E ? p : p - E;
@@ -110,7 +120,7 @@ __global__ void k_csr_keys(const int64_t* __restrict__ edge_index, const int64_t
     bool ok = node >= 0 && node < n_nodes && other >= 0 && other < n_other && rel >= 0 && rel < n_rel;
     if (!ok) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 1);
     bool keep = ok && !(drop_loops && node == other);
-    keys[p] = keep ? uint32_t(node * n_rel + rel) : uint32_t(int64_t(n_nodes) * n_rel);
+    keys[p] = keep ? uint32_t(seg_key(node, rel, n_nodes, n_rel, rel_major)) : uint32_t(int64_t(n_nodes) * n_rel);
     vals[p] = uint32_t(p);
 }
 
@@ -130,7 +140,7 @@ __global__ void k_csr_flags(const int64_t* __restrict__ edge_index, int64_t E, i
 }
 
 // 3. segment table from the scanned flags
-__global__ void k_csr_segments(int64_t entries, uint32_t sentinel, int n_rel, int64_t seg_cap,
+__global__ void k_csr_segments(int64_t entries, uint32_t sentinel, int n_nodes, int n_rel, int rel_major,
                                const uint32_t* __restrict__ keys, const int* __restrict__ seg_index /*excl scan*/,
                                int* __restrict__ seg_ptr, int* __restrict__ seg_node, int* __restrict__ seg_rel,
                                int* __restrict__ counts) {
@@ -146,8 +156,7 @@ __global__ void k_csr_segments(int64_t entries, uint32_t sentinel, int n_rel, in
     if (start) {
         int s = seg_index[p];
         seg_ptr[s] = int(p);
-        seg_node[s] = int(k / uint32_t(n_rel));
-        seg_rel[s] = int(k % uint32_t(n_rel));
+        seg_unkey(k, n_nodes, n_rel, rel_major, seg_node[s], seg_rel[s]);
     }
     // first dropped entry (or the end) terminates the valid range
     bool last_valid = k != sentinel && (p + 1 == entries || keys[p + 1] == sentinel);
@@ -164,18 +173,35 @@ __global__ void k_csr_segments(int64_t entries, uint32_t sentinel, int n_rel, in
 }
 
 // pad the unused tail of the per-segment tables with sentinels so host-sized launches stay simple
-__global__ void k_csr_pad(int64_t seg_cap, int n_nodes, int n_rel, const int* __restrict__ counts,
+// (rkeys, rvals) = keys of the SECONDARY listing: relation for node-major plans, node for relation-major plans
+__global__ void k_csr_pad(int64_t seg_cap, int n_nodes, int n_rel, int rel_major, int* __restrict__ counts,
                           int* __restrict__ seg_node, int* __restrict__ seg_rel, uint32_t* __restrict__ rkeys,
                           uint32_t* __restrict__ rvals) {
     int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (s >= seg_cap) return;
+    if (s == 0) counts[TIPB_CSR_COUNT_REL_MAJOR] = rel_major;
     int S = counts[TIPB_CSR_COUNT_SEGMENTS];
     if (s >= S) {
         seg_node[s] = n_nodes;
         seg_rel[s] = n_rel;
     }
-    rkeys[s] = uint32_t(seg_rel[s]);
+    rkeys[s] = uint32_t(rel_major ? seg_node[s] : seg_rel[s]);
     rvals[s] = uint32_t(s);
+}
+
+// degrees of a relation-major plan: a node's segments are reached through the secondary listing
+__global__ void k_csr_degrees_listed(int n_nodes, const int* __restrict__ node_ptr, const int* __restrict__ listing,
+                                     const int* __restrict__ seg_ptr, int* __restrict__ deg,
+                                     float* __restrict__ inv_deg) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    int d = 0;
+    for (int i = node_ptr[n]; i < node_ptr[n + 1]; ++i) {
+        const int s = listing[i];
+        d += seg_ptr[s + 1] - seg_ptr[s];
+    }
+    deg[n] = d;
+    inv_deg[n] = 1.0f / float(d < 1 ? 1 : d);
 }
 
 // group_ptr[g] = first index i with sorted_keys[i] >= g, for g in [0, n_groups]
@@ -239,96 +265,125 @@ __global__ void k_grp_check_ranges(const int64_t* __restrict__ range_list, int n
     if (!ok) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 2);
 }
 
+// cnt[node*R + r] = entries of segment (node, r); cnt_fwd = the forward-direction share (doubled plans place the
+// reversed copies after the forward ones, so the second pass starts its per-node cursor there)
 __global__ void __launch_bounds__(256)
 k_grp_count(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E, int doubled,
-            int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, int* __restrict__ cnt,
-            int* __restrict__ counts) {
+            int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, int rel_major, int* __restrict__ cnt,
+            int* __restrict__ cnt_fwd, int* __restrict__ counts) {
+    extern __shared__ int s_hist[];  // [2][n_nodes]: both directions, forward only
     const int r = blockIdx.y;
     const int64_t start = range_list[2 * r], end = range_list[2 * r + 1];
+    for (int n = threadIdx.x; n < 2 * n_nodes; n += blockDim.x) s_hist[n] = 0;
+    __syncthreads();
     bool bad = false;
     for (int64_t e = start + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < end; e += int64_t(gridDim.x) * blockDim.x) {
         for (int dir = 0; dir <= doubled; ++dir) {
             int node, other;
-            if (grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, other))
-                atomicAdd(&cnt[int64_t(node) * n_rel + r], 1);
-            else if (!(drop_loops && node == other))
+            if (grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, other)) {
+                atomicAdd(&s_hist[node], 1);
+                if (dir == 0) atomicAdd(&s_hist[n_nodes + node], 1);
+            } else if (!(drop_loops && node == other)) {
                 bad = true;
+            }
         }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < n_nodes; n += blockDim.x) {
+        const int64_t key = seg_key(n, r, n_nodes, n_rel, rel_major);
+        if (s_hist[n]) atomicAdd(&cnt[key], s_hist[n]);
+        if (doubled && s_hist[n_nodes + n]) atomicAdd(&cnt_fwd[key], s_hist[n_nodes + n]);
     }
     if (bad) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 1);
 }
 
 constexpr int GRP_ROUNDS = 16;
 
+// One CTA per (relation, direction).  A tile is WARPS x 16 rounds x 32 consecutive edges; every thread first
+// pulls its 16 edges into registers (one memory round trip), then the tile is ranked twice over the registers:
+// per-warp per-node counts -> prefix over warps + running per-node cursor -> stable positions.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E, int doubled,
-              int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, const int* __restrict__ seg_start,
-              int* __restrict__ eid, int* __restrict__ other_out) {
+k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E,
+              int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, int rel_major,
+              const int* __restrict__ seg_start, const int* __restrict__ cnt_fwd, int* __restrict__ eid,
+              int* __restrict__ other_out) {
     extern __shared__ int sm_i[];
     int* wh = sm_i;                        // [WARPS][n_nodes]
     int* cursor = sm_i + WARPS * n_nodes;  // [n_nodes]
-    const int r = blockIdx.x;
+    const int r = blockIdx.x, dir = blockIdx.y;
     const int w = warp_id(), lane = lane_id();
     const int64_t start = range_list[2 * r], end = range_list[2 * r + 1];
-    for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32) cursor[n] = 0;
+    for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32)
+        cursor[n] = dir ? cnt_fwd[seg_key(n, r, n_nodes, n_rel, rel_major)] : 0;
     constexpr int TILE = WARPS * 32 * GRP_ROUNDS;
-    for (int dir = 0; dir <= doubled; ++dir) {
-        for (int64_t tile = start; tile < end; tile += TILE) {
-            for (int i = threadIdx.x; i < WARPS * n_nodes; i += WARPS * 32) wh[i] = 0;
-            __syncthreads();
-            const int64_t wbase = tile + int64_t(w) * 32 * GRP_ROUNDS;
-            for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
-                const int64_t e = wbase + rd * 32 + lane;
-                int node = 0, oth = 0;
-                const bool valid = e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, oth);
-                const unsigned act = __ballot_sync(FULL, valid);
-                if (valid) {
-                    const unsigned peers = __match_any_sync(act, node);
-                    if ((__ffs(peers) - 1) == lane) wh[w * n_nodes + node] += __popc(peers);
-                }
-                __syncwarp();
-            }
-            __syncthreads();
-            for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32) {
-                int run = cursor[n];
+    for (int64_t tile = start; tile < end; tile += TILE) {
+        for (int i = threadIdx.x; i < WARPS * n_nodes; i += WARPS * 32) wh[i] = 0;
+        const int64_t wbase = tile + int64_t(w) * 32 * GRP_ROUNDS;
+        int node[GRP_ROUNDS], oth[GRP_ROUNDS], base[GRP_ROUNDS];
+        unsigned vmask = 0;
 #pragma unroll
-                for (int ww = 0; ww < WARPS; ++ww) {
-                    const int c = wh[ww * n_nodes + n];
-                    wh[ww * n_nodes + n] = run;
-                    run += c;
-                }
-                cursor[n] = run;
-            }
-            __syncthreads();
-            for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
-                const int64_t e = wbase + rd * 32 + lane;
-                int node = 0, oth = 0;
-                const bool valid = e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, oth);
-                const unsigned act = __ballot_sync(FULL, valid);
-                unsigned peers = 0;
-                int pos = 0;
-                if (valid) {
-                    peers = __match_any_sync(act, node);
-                    pos = seg_start[int64_t(node) * n_rel + r] + wh[w * n_nodes + node] + __popc(peers & ((1u << lane) - 1u));
-                }
-                __syncwarp();
-                if (valid && (__ffs(peers) - 1) == lane) wh[w * n_nodes + node] += __popc(peers);
-                __syncwarp();
-                if (valid) {
-                    eid[pos] = int(dir ? E + e : e);
-                    other_out[pos] = oth;
-                }
-            }
-            __syncthreads();
+        for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
+            const int64_t e = wbase + rd * 32 + lane;
+            node[rd] = 0;
+            oth[rd] = 0;
+            if (e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node[rd], oth[rd]))
+                vmask |= 1u << rd;
         }
+#pragma unroll
+        for (int rd = 0; rd < GRP_ROUNDS; ++rd)
+            base[rd] = (vmask >> rd) & 1u ? seg_start[seg_key(node[rd], r, n_nodes, n_rel, rel_major)] : 0;
+        __syncthreads();
+#pragma unroll
+        for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
+            const bool valid = (vmask >> rd) & 1u;
+            const unsigned act = __ballot_sync(FULL, valid);
+            if (valid) {
+                const unsigned peers = __match_any_sync(act, node[rd]);
+                if ((__ffs(peers) - 1) == lane) wh[w * n_nodes + node[rd]] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int n = threadIdx.x; n < n_nodes; n += WARPS * 32) {
+            int run = cursor[n];
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ++ww) {
+                const int c = wh[ww * n_nodes + n];
+                wh[ww * n_nodes + n] = run;
+                run += c;
+            }
+            cursor[n] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
+            const bool valid = (vmask >> rd) & 1u;
+            const unsigned act = __ballot_sync(FULL, valid);
+            unsigned peers = 0;
+            int pos = 0;
+            if (valid) {
+                peers = __match_any_sync(act, node[rd]);
+                pos = base[rd] + wh[w * n_nodes + node[rd]] + __popc(peers & ((1u << lane) - 1u));
+            }
+            __syncwarp();
+            if (valid && (__ffs(peers) - 1) == lane) wh[w * n_nodes + node[rd]] += __popc(peers);
+            __syncwarp();
+            if (valid) {
+                const int64_t e = wbase + rd * 32 + lane;
+                eid[pos] = int(dir ? E + e : e);
+                other_out[pos] = oth[rd];
+            }
+        }
+        __syncthreads();
     }
 }
 
 // dense key space -> compact segment table
 __global__ void k_grp_segments(const int* __restrict__ cnt, const int* __restrict__ seg_start,
-                               const int* __restrict__ seg_index, int64_t n_keys, int n_rel, int* __restrict__ seg_ptr,
-                               int* __restrict__ seg_node, int* __restrict__ seg_rel, int* __restrict__ counts) {
+                               const int* __restrict__ seg_index, int64_t n_keys, int n_nodes, int n_rel, int rel_major,
+                               int* __restrict__ seg_ptr, int* __restrict__ seg_node, int* __restrict__ seg_rel,
+                               int* __restrict__ counts) {
     int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q > n_keys) return;
     if (q == n_keys) {
@@ -341,8 +396,7 @@ __global__ void k_grp_segments(const int* __restrict__ cnt, const int* __restric
     if (cnt[q] > 0) {
         const int s = seg_index[q];
         seg_ptr[s] = seg_start[q];
-        seg_node[s] = int(q / n_rel);
-        seg_rel[s] = int(q % n_rel);
+        seg_unkey(uint32_t(q), n_nodes, n_rel, rel_major, seg_node[s], seg_rel[s]);
     }
 }
 
@@ -375,8 +429,8 @@ size_t csr_build_ws_bytes(int64_t entries, int64_t n_nodes, int64_t n_rel) {
 }
 
 int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list, int64_t E,
-              int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled, int drop_loops, void* plan,
-              void* ws, cudaStream_t s) {
+              int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled, int drop_loops, int rel_major,
+              void* plan, void* ws, cudaStream_t s) {
     const int64_t entries = doubled ? 2 * E : E;
     CsrView v = csr_view(plan, entries, n_nodes, n_rel);
     const uint32_t sentinel = uint32_t(n_nodes * n_rel);
@@ -400,49 +454,66 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
         const int64_t n_keys = n_nodes * n_rel;
         int* cnt = reinterpret_cast<int*>(k0);
         int* seg_start = reinterpret_cast<int*>(v0);
+        int* cnt_fwd = reinterpret_cast<int*>(k1);
         int* seg_index = flags;
         TIPB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (n_keys + 1) * sizeof(int), s));
+        if (doubled) TIPB_CHECK_CUDA(cudaMemsetAsync(cnt_fwd, 0, (n_keys + 1) * sizeof(int), s));
         k_grp_check_ranges<<<(unsigned)ceil_div(n_rel, T), T, 0, s>>>(range_list, (int)n_rel, E, v.counts);
-        k_grp_count<<<dim3(8, (unsigned)n_rel), 256, 0, s>>>(edge_index, range_list, E, doubled, (int)n_nodes, (int)n_other,
-                                                            (int)n_rel, by_src, drop_loops, cnt, v.counts);
+        {
+            const size_t hsm = size_t(2) * n_nodes * sizeof(int);
+            if ((rc = ensure_dyn_smem((const void*)k_grp_count, hsm))) return rc;
+            k_grp_count<<<dim3(4, (unsigned)n_rel), 256, hsm, s>>>(edge_index, range_list, E, doubled, (int)n_nodes,
+                                                                  (int)n_other, (int)n_rel, by_src, drop_loops,
+                                                                  rel_major, cnt, cnt_fwd, v.counts);
+        }
         if ((rc = exclusive_scan_i32(cnt, seg_start, n_keys, scan_ws, s))) return rc;
         k_flag_positive<<<(unsigned)ceil_div(n_keys, T), T, 0, s>>>(cnt, n_keys, seg_index);
         if ((rc = exclusive_scan_i32(seg_index, seg_index, n_keys, scan_ws, s))) return rc;
-        k_grp_segments<<<(unsigned)ceil_div(n_keys + 1, T), T, 0, s>>>(cnt, seg_start, seg_index, n_keys, (int)n_rel,
-                                                                       v.seg_ptr, v.seg_node, v.seg_rel, v.counts);
+        k_grp_segments<<<(unsigned)ceil_div(n_keys + 1, T), T, 0, s>>>(cnt, seg_start, seg_index, n_keys, (int)n_nodes,
+                                                                       (int)n_rel, rel_major, v.seg_ptr, v.seg_node,
+                                                                       v.seg_rel, v.counts);
         const int warps = grp_warps(n_nodes);
         const size_t smem = size_t(warps + 1) * n_nodes * sizeof(int);
 #define GRP_SCATTER(WV)                                                                                             \
         {                                                                                                           \
             auto kern = k_grp_scatter<WV>;                                                                          \
             if ((rc = ensure_dyn_smem((const void*)kern, smem))) return rc;                                         \
-            kern<<<(unsigned)n_rel, WV * 32, smem, s>>>(edge_index, range_list, E, doubled, (int)n_nodes,           \
-                                                        (int)n_other, (int)n_rel, by_src, drop_loops, seg_start,    \
-                                                        v.eid, v.other);                                            \
+            kern<<<dim3((unsigned)n_rel, doubled ? 2 : 1), WV * 32, smem, s>>>(                                      \
+                edge_index, range_list, E, (int)n_nodes, (int)n_other, (int)n_rel, by_src, drop_loops, rel_major,   \
+                seg_start, cnt_fwd, v.eid, v.other);                                                                \
         }
         if (warps == 8) GRP_SCATTER(8) else if (warps == 4) GRP_SCATTER(4) else GRP_SCATTER(2)
 #undef GRP_SCATTER
     } else if (entries > 0) {
         unsigned g = (unsigned)ceil_div(entries, T);
         k_csr_keys<<<g, T, 0, s>>>(edge_index, edge_type, range_list, E, entries, (int)n_nodes, (int)n_other,
-                                    (int)n_rel, by_src, drop_loops, k0, v0, v.counts);
+                                    (int)n_rel, by_src, drop_loops, rel_major, k0, v0, v.counts);
         if ((rc = sort_pairs_u32(k0, v0, k1, v1, entries, bits_for(sentinel), sort_ws, s))) return rc;
         k_copy_u32_to_i32<<<g, T, 0, s>>>(v1, v.eid, entries);
         k_csr_flags<<<g, T, 0, s>>>(edge_index, E, entries, by_src, sentinel, k1, v.eid, v.other, flags);
         if ((rc = exclusive_scan_i32(flags, flags, entries, scan_ws, s))) return rc;
-        k_csr_segments<<<(unsigned)ceil_div(entries + 1, T), T, 0, s>>>(entries, sentinel, (int)n_rel, v.seg_cap, k1,
-                                                                        flags, v.seg_ptr, v.seg_node, v.seg_rel,
-                                                                        v.counts);
+        k_csr_segments<<<(unsigned)ceil_div(entries + 1, T), T, 0, s>>>(entries, sentinel, (int)n_nodes, (int)n_rel,
+                                                                        rel_major, k1, flags, v.seg_ptr, v.seg_node,
+                                                                        v.seg_rel, v.counts);
     }
-    // relation-major listing of the segments
+    // primary group pointers (direct segment ranges) and the secondary listing (segment ids grouped the other way)
     unsigned gs = (unsigned)ceil_div(v.seg_cap, T);
-    k_csr_pad<<<gs, T, 0, s>>>(v.seg_cap, (int)n_nodes, (int)n_rel, v.counts, v.seg_node, v.seg_rel, k0, v0);
-    k_group_ptr<int><<<(unsigned)ceil_div(v.seg_cap + 1, T), T, 0, s>>>(v.seg_node, v.seg_cap, (int)n_nodes,
-                                                                          v.node_ptr);
-    k_csr_degrees<<<(unsigned)ceil_div(n_nodes, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.seg_ptr, v.deg, v.inv_deg);
-    if ((rc = sort_pairs_u32(k0, v0, k1, v1, v.seg_cap, bits_for((uint64_t)n_rel), sort_ws, s))) return rc;
-    k_copy_u32_to_i32<<<gs, T, 0, s>>>(v1, v.rel_seg, v.seg_cap);
-    k_group_ptr<uint32_t><<<(unsigned)ceil_div(v.seg_cap + 1, T), T, 0, s>>>(k1, v.seg_cap, (int)n_rel, v.rel_seg_ptr);
+    unsigned gp = (unsigned)ceil_div(v.seg_cap + 1, T);
+    k_csr_pad<<<gs, T, 0, s>>>(v.seg_cap, (int)n_nodes, (int)n_rel, rel_major, v.counts, v.seg_node, v.seg_rel, k0, v0);
+    if (rel_major) {
+        k_group_ptr<int><<<gp, T, 0, s>>>(v.seg_rel, v.seg_cap, (int)n_rel, v.rel_seg_ptr);
+        if ((rc = sort_pairs_u32(k0, v0, k1, v1, v.seg_cap, bits_for((uint64_t)n_nodes), sort_ws, s))) return rc;
+        k_copy_u32_to_i32<<<gs, T, 0, s>>>(v1, v.rel_seg, v.seg_cap);
+        k_group_ptr<uint32_t><<<gp, T, 0, s>>>(k1, v.seg_cap, (int)n_nodes, v.node_ptr);
+        k_csr_degrees_listed<<<(unsigned)ceil_div(n_nodes, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.rel_seg, v.seg_ptr,
+                                                                          v.deg, v.inv_deg);
+    } else {
+        k_group_ptr<int><<<gp, T, 0, s>>>(v.seg_node, v.seg_cap, (int)n_nodes, v.node_ptr);
+        k_csr_degrees<<<(unsigned)ceil_div(n_nodes, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.seg_ptr, v.deg, v.inv_deg);
+        if ((rc = sort_pairs_u32(k0, v0, k1, v1, v.seg_cap, bits_for((uint64_t)n_rel), sort_ws, s))) return rc;
+        k_copy_u32_to_i32<<<gs, T, 0, s>>>(v1, v.rel_seg, v.seg_cap);
+        k_group_ptr<uint32_t><<<gp, T, 0, s>>>(k1, v.seg_cap, (int)n_rel, v.rel_seg_ptr);
+    }
     TIPB_CHECK_LAUNCH("typed_csr_build");
     return TIPB_OK;
 }
@@ -469,7 +540,8 @@ int tipb_typed_csr_layout(int64_t n_entries, int64_t n_nodes, int64_t n_rel, int
 
 int tipb_typed_csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list,
                          int64_t n_edges, int64_t n_nodes, int64_t n_other, int64_t n_rel, int by_src, int doubled,
-                         int drop_self_loops, void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream) {
+                         int drop_self_loops, int rel_major, void* plan, size_t plan_bytes, void* ws, size_t ws_bytes,
+                         void* stream) {
     TIPB_CHECK_ARG(n_edges >= 0 && n_nodes > 0 && n_other > 0 && n_rel > 0, "typed_csr_build: bad sizes");
     const int64_t entries = doubled ? 2 * n_edges : n_edges;
     TIPB_CHECK_ARG(entries < (int64_t(1) << 31) - 2, "typed_csr_build: too many entries for int32 indexing");
@@ -479,6 +551,6 @@ int tipb_typed_csr_build(const int64_t* edge_index, const int64_t* edge_type, co
     TIPB_CHECK_ARG(plan && plan_bytes >= tipb_typed_csr_bytes(entries, n_nodes, n_rel), "typed_csr_build: plan buffer too small");
     TIPB_CHECK_ARG(ws && ws_bytes >= tipb_typed_csr_workspace_bytes(entries, n_nodes, n_rel), "typed_csr_build: workspace too small");
     return tipb::csr_build(edge_index, edge_type, range_list, n_edges, n_nodes, n_other, n_rel, by_src, doubled,
-                           drop_self_loops, plan, ws, (cudaStream_t)stream);
+                           drop_self_loops, rel_major != 0, plan, ws, (cudaStream_t)stream);
 }
 }

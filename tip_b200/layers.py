@@ -366,7 +366,7 @@ class TIP(nn.Module):
         if self._neg_index is None:
             self._neg_index = torch.empty_like(d.dd_train_idx)
             self._neg_plan = ops.TypedCSR(d.dd_train_idx.shape[1], d.n_drug, d.n_dd_et, self.device, by_src=False,
-                                          doubled=True)
+                                          doubled=True, rel_major=True)
             self._side = torch.cuda.Stream(device=self.device)
         # the negatives do not depend on the encoder: sample and index them on a side stream meanwhile
         cur = torch.cuda.current_stream(self.device)
@@ -378,7 +378,7 @@ class TIP(nn.Module):
         self.embeddings = self._encode()
         cur.wait_stream(self._side)
         pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False,
-                                   doubled=True)
+                                   doubled=True, rel_major=True)
         # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient
         return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan)
 

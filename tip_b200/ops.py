@@ -52,10 +52,11 @@ class TypedCSR(object):
     """Device-side index structure built by tipb_typed_csr_build (tip_b200/csrc/typed_csr.cu)."""
 
     def __init__(self, n_edges, n_nodes, n_rel, device, by_src=False, doubled=False, drop_self_loops=False,
-                 n_other=None):
+                 n_other=None, rel_major=False):
         self.n_edges, self.n_nodes, self.n_rel = int(n_edges), int(n_nodes), int(n_rel)
         self.n_other = int(n_other if n_other is not None else n_nodes)
         self.by_src, self.doubled, self.drop_self_loops = bool(by_src), bool(doubled), bool(drop_self_loops)
+        self.rel_major = bool(rel_major)   # segments ordered (relation, node): decoder plans
         self.n_entries = self.n_edges * (2 if doubled else 1)
         self.device = device
         L = lib()
@@ -72,8 +73,8 @@ class TypedCSR(object):
         ws = workspace(self._ws_bytes, self.device, "csr")
         check(lib().tipb_typed_csr_build(ptr(edge_index), ptr(edge_type), ptr(range_list), self.n_edges, self.n_nodes,
                                          self.n_other, self.n_rel, int(self.by_src), int(self.doubled),
-                                         int(self.drop_self_loops), ptr(self.buf), self.nbytes, ptr(ws), ws.numel(),
-                                         stream()), "typed_csr_build")
+                                         int(self.drop_self_loops), int(self.rel_major), ptr(self.buf), self.nbytes,
+                                         ptr(ws), ws.numel(), stream()), "typed_csr_build")
         return self
 
     # ---- views (tests, inv_deg for the backward pass)
@@ -295,7 +296,7 @@ class _DecoderFunction(torch.autograd.Function):
         z, weight, edge_index, edge_type = ctx.saved_tensors
         grad_out = _f32c(grad_out)
         n_edges, n_nodes, n_rel, dim = edge_index.shape[1], z.shape[0], weight.shape[0], z.shape[1]
-        plan = cached_plan(edge_index, n_nodes, n_rel, edge_type=edge_type, validate=False, by_src=False, doubled=True)
+        plan = cached_plan(edge_index, n_nodes, n_rel, edge_type=edge_type, validate=False, by_src=False, doubled=True, rel_major=True)
         L = lib()
         d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
         ws = workspace(L.tipb_decoder_workspace_bytes(n_edges, n_nodes, n_rel, dim), z.device)
