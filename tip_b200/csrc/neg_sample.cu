@@ -154,6 +154,10 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
     }
     const uint32_t* bits = member + int64_t(r) * words_per_rel;
     const int n_acc = *n_accepted_ptr;
+    if (n_acc <= 0) {  // no usable stream at all
+        for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = -1;
+        return;
+    }
     int* nhi = NHI + win_off;
     int* pr = PR + win_off;
     if (threadIdx.x == 0) s_carry = 0;
@@ -163,10 +167,20 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
         const int x0 = base + threadIdx.x * ITEMS;
         int nh[ITEMS];
         int local = 0;
+        // unconditional (clamped) loads first, so the four value loads and then the four bitmap probes overlap
+        int val[ITEMS];
+        uint32_t word[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int j = lo + x0 + i;
+            val[i] = A[j < n_acc ? j : max(n_acc - 1, 0)];
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) word[i] = bits[val[i] >> 5];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int x = x0 + i, j = lo + x;
-            nh[i] = (x < L && j < n_acc && !is_member(bits, A[j])) ? 1 : 0;
+            nh[i] = (x < L && j < n_acc && !((word[i] >> (val[i] & 31)) & 1u)) ? 1 : 0;
             local += nh[i];
         }
         // block-wide exclusive scan of `local`
@@ -211,14 +225,20 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
     }
 }
 
-// One warp follows o_{r+1} = F_r[o_r - lo_r].  Lane 0 does the dependent lookups; the other lanes pull the part of
-// F_{r+AHEAD} that the walk is going to need into L1: given o_r the start of relation r+AHEAD is known to within a
-// few hundred entries (pred[] = expected start offsets), far tighter than the bracket itself.
-constexpr int WALK_AHEAD = 16;
+// One warp follows o_{r+1} = F_r[o_r - lo_r].  Lane 0 does the dependent lookups out of shared memory: all
+// lanes keep staging, with cp.async, the 2 KB of F_{r+AHEAD} around the offset the walk is going to need --
+// given o_r, the start of relation r+AHEAD is known to within a few hundred entries (pred[] = expected start
+// offsets), far tighter than the bracket itself.  A lookup that falls outside its staged window (never seen
+// in practice) simply goes to global memory.
+constexpr int WALK_AHEAD = 8;
+constexpr int WALK_WIN = 512;  // ints staged per relation
 __global__ void __launch_bounds__(32)
 k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n_rel, int* __restrict__ off,
              int* __restrict__ chain_out, int* __restrict__ status) {
-    extern __shared__ int s_tab[];  // per relation: lo, W, f_off (fits 32 bits), k, pred
+    extern __shared__ int4 s_walk4[];
+    int* ring = reinterpret_cast<int*>(s_walk4);            // [AHEAD+1][WALK_WIN]
+    int* slot_g0 = ring + (WALK_AHEAD + 1) * WALK_WIN;      // [AHEAD+1] first absolute F index held by a slot
+    int* s_tab = slot_g0 + 16;                              // per relation: lo, W, f_off (fits 32 bits), k, pred
     const int lane = threadIdx.x;
     for (int i = lane; i < n_rel; i += 32) {
         const int64_t* tb = table + int64_t(i) * TAB;
@@ -229,25 +249,41 @@ k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n
         s_tab[5 * i + 4] = int(tb[6]);
     }
     __syncwarp();
+    // stage the window of relation `ra`, predicted from offset `o_now` of relation `r_now`; always commits a group
+    auto stage = [&](int ra, int r_now, int o_now) {
+        if (ra < n_rel) {
+            const int xp = o_now + (s_tab[5 * ra + 4] - s_tab[5 * r_now + 4]) - s_tab[5 * ra] - WALK_WIN / 2;
+            const int xc = min(max(xp, 0), max(s_tab[5 * ra + 1] - WALK_WIN, 0));
+            const int g0 = (s_tab[5 * ra + 2] + xc) & ~3;   // 16-byte aligned absolute index
+            const int slot = ra % (WALK_AHEAD + 1);
+            if (lane == 0) slot_g0[slot] = g0;
+            int* dst = ring + slot * WALK_WIN;
+            for (int c = lane; c < WALK_WIN / 4; c += 32) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 4 * c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(F + g0 + 4 * c));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    for (int ra = 0; ra < WALK_AHEAD; ++ra) stage(ra, 0, 0);
     int o = 0;
     int r = 0;
     int fail = 0;
     for (; r < n_rel; ++r) {
-        if (lane > 0) {
-            const int ra = r + WALK_AHEAD;
-            if (ra < n_rel) {
-                const int xp = o + (s_tab[5 * ra + 4] - s_tab[5 * r + 4]) - s_tab[5 * ra] + (lane - 16) * 32;
-                const int xc = min(max(xp, 0), s_tab[5 * ra + 1] - 1);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(F + s_tab[5 * ra + 2] + xc));
-            }
-        } else {
+        stage(r + WALK_AHEAD, r, o);
+        asm volatile("cp.async.wait_group %0;" ::"n"(WALK_AHEAD));
+        __syncwarp();
+        if (lane == 0) {
             off[r] = o;
             if (s_tab[5 * r + 3] != 0) {
                 const int x = o - s_tab[5 * r];
                 if (x < 0 || x >= s_tab[5 * r + 1]) {
                     fail = NEG_STATUS_BRACKET_MISS;
                 } else {
-                    const int nxt = F[s_tab[5 * r + 2] + x];
+                    const int g = s_tab[5 * r + 2] + x;
+                    const int slot = r % (WALK_AHEAD + 1);
+                    const int d = g - slot_g0[slot];
+                    const int nxt = (d >= 0 && d < WALK_WIN) ? ring[slot * WALK_WIN + d] : F[g];
                     if (nxt < 0) fail = NEG_STATUS_OUT_OF_WORDS; else o = nxt;
                 }
             }
@@ -256,6 +292,7 @@ k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n
         if (fail) break;
         o = __shfl_sync(FULL, o, 0);
     }
+    asm volatile("cp.async.wait_group 0;");
     if (lane == 0) {
         if (fail) atomicOr(status, fail);
         for (int q = r; q < n_rel; ++q) off[q] = -1;  // relations that could not be placed (r == n_rel: none)
@@ -507,7 +544,7 @@ static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t n_words, int
     t.Apos = c.take<int>(n_words + 2);
     t.NHI = c.take<int>(sum_l + 1);
     t.PR = c.take<int>(sum_l + 1);
-    t.F = c.take<int>(sum_w + 1);
+    t.F = c.take<int>(sum_w + 1024);  // slack: the chain walk stages 2 KB windows with 16-byte copies
     t.off = c.take<int>(n_rel + 1);
     t.chain_out = c.take<int>(4);
     t.perm = c.take<int>(n_edges + 1);
@@ -618,7 +655,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     TIPB_CHECK_ARG(exact_mode || table, "neg_sample: the fast path needs the bracket table");
     TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample: n_nodes must be in [2, 46340]");
     TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample: bad stream length");
-    TIPB_CHECK_ARG(n_rel > 0 && n_rel * 20 <= 200 * 1024, "neg_sample: n_rel out of range");
+    TIPB_CHECK_ARG(n_rel > 0 && n_rel * 20 <= 180 * 1024, "neg_sample: n_rel out of range");
     TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
                    "neg_sample: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
@@ -644,7 +681,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
     } else {
         k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
-        const size_t smem = size_t(n_rel) * 20;
+        const size_t smem = size_t(n_rel) * 20 + size_t((WALK_AHEAD + 1) * WALK_WIN + 16) * sizeof(int);
         if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
         k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
         if (n_edges > 0)

@@ -297,13 +297,13 @@ k_grp_count(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ 
     if (bad) atomicOr(&counts[TIPB_CSR_COUNT_STATUS], 1);
 }
 
-constexpr int GRP_ROUNDS = 16;
+constexpr int GRP_ROUNDS = 8;
 
 // One CTA per (relation, direction).  A tile is WARPS x 16 rounds x 32 consecutive edges; every thread first
 // pulls its 16 edges into registers (one memory round trip), then the tile is ranked twice over the registers:
 // per-warp per-node counts -> prefix over warps + running per-node cursor -> stable positions.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 3 : 1)
 k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t E,
               int n_nodes, int n_other, int n_rel, int by_src, int drop_loops, int rel_major,
               const int* __restrict__ seg_start, const int* __restrict__ cnt_fwd, int* __restrict__ eid,
@@ -322,13 +322,28 @@ k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict_
         const int64_t wbase = tile + int64_t(w) * 32 * GRP_ROUNDS;
         int node[GRP_ROUNDS], oth[GRP_ROUNDS], base[GRP_ROUNDS];
         unsigned vmask = 0;
+        // two batches of eight rounds: all sixteen 64-bit loads of a batch are issued before any is consumed
+        // (clamped addresses keep them unconditional), so a tile costs two memory round trips, not sixteen
+        const bool pick_a = (by_src != 0) != (dir != 0);
 #pragma unroll
-        for (int rd = 0; rd < GRP_ROUNDS; ++rd) {
-            const int64_t e = wbase + rd * 32 + lane;
-            node[rd] = 0;
-            oth[rd] = 0;
-            if (e < end && grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node[rd], oth[rd]))
-                vmask |= 1u << rd;
+        for (int half = 0; half < GRP_ROUNDS; half += 8) {
+            int64_t ra[8], rb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t e = wbase + (half + j) * 32 + lane;
+                const int64_t ec = e < end ? e : end - 1;
+                ra[j] = edge_index[ec];
+                rb[j] = edge_index[E + ec];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t e = wbase + (half + j) * 32 + lane;
+                const int64_t nd = pick_a ? ra[j] : rb[j], ot = pick_a ? rb[j] : ra[j];
+                node[half + j] = int(nd);
+                oth[half + j] = int(ot);
+                if (e < end && nd >= 0 && nd < n_nodes && ot >= 0 && ot < n_other && !(drop_loops && nd == ot))
+                    vmask |= 1u << (half + j);
+            }
         }
 #pragma unroll
         for (int rd = 0; rd < GRP_ROUNDS; ++rd)
