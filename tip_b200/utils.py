@@ -52,7 +52,7 @@ def process_edges(raw_edge_list, p=0.9):
 def sparse_id(n):
     """n x n sparse COO identity, float32  (src/utils.py:68-75)"""
     i = torch.arange(n, dtype=torch.long)
-    return torch.sparse_coo_tensor(torch.stack([i, i]), torch.ones(n, dtype=torch.float32), (n, n))
+    return torch.sparse_coo_tensor(torch.stack([i, i]), torch.ones(n, dtype=torch.float32), (n, n), check_invariants=False)
 
 
 def dense_id(n):
