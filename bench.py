@@ -220,7 +220,8 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     from tip_b200 import layers, neg_sampling as ns
 
     data, workload = make_data(args.shape)
@@ -232,7 +233,8 @@ def run_b200_arm(args):
         model = parallel.ShardedTIP(settings_for(args.mod), dev, mod=args.mod, data=data, rank=rank, world=world)
     else:
         model = layers.TIP(settings_for(args.mod), dev, mod=args.mod, data=data)
-    opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True,
+                           fused=os.environ.get("TIPB_BENCH_FUSED_ADAM", "1") == "1")
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -306,7 +308,7 @@ def run_b200_arm(args):
     e2e = None
     if world == 1:
         e2e = measure_e2e(model, opt, data, args.steps, e_total)
-    launches, launches_all = count_library_launches(step) if rank == 0 else (0, 0)
+    launches, launches_all = count_library_launches(step)   # every rank runs it: the step contains collectives
 
     if rank == 0:
         k_time, alg_bytes, compulsory, n_seg = measure_dominant_kernel(model, max(args.steps, 10))
@@ -341,7 +343,12 @@ def run_b200_arm(args):
                 "all_cuda_kernels_per_step": launches_all, "loss": loss_value}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing NCCL down while captured CUDA graphs still reference the communicator can block; every
+        # rank is past its last collective here, so synchronise on the device and leave without the teardown.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def measure_e2e(model, opt, data, steps, e_total):
@@ -353,9 +360,8 @@ def measure_e2e(model, opt, data, steps, e_total):
     d = model.data
 
     def e2e_step():
-        for k in names:                       # host -> device, in place (bumps the tensor version => plans are rebuilt)
-            getattr(d, k).copy_(host[k], non_blocking=True)
-        ops.clear_plan_cache()
+        for k in names:                       # host -> device, in place: the version bump makes every cached typed CSR /
+            getattr(d, k).copy_(host[k], non_blocking=True)   # bitmap rebuild itself (into the same buffers)
         model.invalidate_graph_caches()
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)

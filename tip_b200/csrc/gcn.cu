@@ -17,32 +17,71 @@ namespace tipb {
 
 // out[n] = post( scale_out[n] * ( sum_{p in node n} scale_in[other[p]] * x[other[p]] + self * scale_in[n] * x[n] ) )
 // rows are nodes [node_lo, node_hi) of the plan; output row index is n - node_lo.
+constexpr int HUB_DEGREE = 256;  // rows longer than this are split over the eight warps of their CTA
+
+template <int LPR>
+__device__ __forceinline__ void node_epilogue(float4 a, int n, int l, const float* __restrict__ scale_out,
+                                              const float* __restrict__ scale_in, const float4* __restrict__ x,
+                                              const float4* __restrict__ bias, int node_lo, int self_term, int relu,
+                                              float4* __restrict__ out) {
+    if (self_term) {
+        const float si = scale_in ? scale_in[n] : 1.f;
+        a = f4_fma(si, x[int64_t(n) * LPR + l], a);
+    }
+    if (scale_out) {
+        const float so = scale_out[n];
+        a.x *= so; a.y *= so; a.z *= so; a.w *= so;
+    }
+    if (bias) a = f4_add(a, bias[l]);
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    out[int64_t(n - node_lo) * LPR + l] = a;
+}
+
+// Each CTA owns eight consecutive rows.  Short rows: one warp per row.  Hub rows (the P-P graph has proteins
+// with thousands of neighbours) would serialise on one warp, so all eight warps take an eighth of the row each
+// and the partial sums are added in warp order (fixed order => deterministic).
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_node_aggregate(const int* __restrict__ node_ptr, const int* __restrict__ seg_ptr, const int* __restrict__ other,
                  const float* __restrict__ scale_out, const float* __restrict__ scale_in, const float4* __restrict__ x,
                  const float4* __restrict__ bias, int node_lo, int node_hi, int self_term, int relu,
                  float4* __restrict__ out) {
-    const int lane = lane_id();
+    __shared__ float4 part[8][LPR];
+    __shared__ int s_beg[8], s_end[8];
+    const int lane = lane_id(), w = warp_id();
     const int g = lane / LPR, l = lane % LPR;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int n = node_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); n < node_hi; n += n_warps) {
-        const int beg = seg_ptr[node_ptr[n]], end = seg_ptr[node_ptr[n + 1]];
-        const int idx = (beg + lane < end) ? ld_stream_i32(other + beg + lane) : 0;
-        float4 a = warp_gather_sum<LPR, false>(x, other, scale_in, beg, end, idx);
-        if (g == 0) {
-            if (self_term) {
-                const float si = scale_in ? scale_in[n] : 1.f;
-                a = f4_fma(si, x[int64_t(n) * LPR + l], a);
-            }
-            if (scale_out) {
-                const float so = scale_out[n];
-                a.x *= so; a.y *= so; a.z *= so; a.w *= so;
-            }
-            if (bias) a = f4_add(a, bias[l]);
-            if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-            out[int64_t(n - node_lo) * LPR + l] = a;
+    for (int n0 = node_lo + blockIdx.x * 8; n0 < node_hi; n0 += gridDim.x * 8) {
+        const int n = n0 + w;
+        int beg = 0, end = 0;
+        if (n < node_hi) {
+            beg = seg_ptr[node_ptr[n]];
+            end = seg_ptr[node_ptr[n + 1]];
         }
+        if (lane == 0) { s_beg[w] = beg; s_end[w] = end; }
+        if (n < node_hi && end - beg <= HUB_DEGREE) {
+            const int idx = (beg + lane < end) ? ld_stream_i32(other + beg + lane) : 0;
+            const float4 a = warp_gather_sum<LPR, false>(x, other, scale_in, beg, end, idx);
+            if (g == 0) node_epilogue<LPR>(a, n, l, scale_out, scale_in, x, bias, node_lo, self_term, relu, out);
+        }
+        __syncthreads();
+        for (int h = 0; h < 8; ++h) {            // CTA-uniform: every warp sees the same row bounds
+            const int hb = s_beg[h], he = s_end[h];
+            if (he - hb <= HUB_DEGREE) continue;
+            const int chunk = (he - hb + 7) >> 3;
+            const int cb = min(hb + w * chunk, he), ce = min(cb + chunk, he);
+            const int idx = (cb + lane < ce) ? ld_stream_i32(other + cb + lane) : 0;
+            const float4 a = warp_gather_sum<LPR, false>(x, other, scale_in, cb, ce, idx);
+            if (g == 0) part[w][l] = a;
+            __syncthreads();
+            if (w == 0 && g == 0) {
+                float4 t = part[0][l];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) t = f4_add(t, part[k][l]);
+                node_epilogue<LPR>(t, n0 + h, l, scale_out, scale_in, x, bias, node_lo, self_term, relu, out);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
     }
 }
 

@@ -119,6 +119,12 @@ class _Membership(object):
     """per-relation bitmaps of the positive pairs, their popcounts, and the bracket table"""
 
     def __init__(self, pos_edge_index, num_nodes, range_list):
+        self.member = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=pos_edge_index.device)
+        self.build(pos_edge_index, num_nodes, range_list)
+
+    def build(self, pos_edge_index, num_nodes, range_list):
+        """(re)build bitmaps, popcounts and the bracket table; device buffers are reused when the sizes match"""
         L = lib()
         dev = pos_edge_index.device
         self.n_edges = int(pos_edge_index.shape[1])
@@ -133,7 +139,8 @@ class _Membership(object):
         nbytes = L.tipb_neg_bitmap_bytes(num_nodes, max(self.n_rel, 1))
         if nbytes > (24 << 30):
             raise _lib.TipbError(f"positive-pair bitmaps would need {nbytes >> 30} GiB")
-        self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)
+        if self.member is None or self.member.numel() != max(nbytes // 4, 1):
+            self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)
         popcount = torch.zeros(max(self.n_rel, 1), dtype=torch.int32, device=dev)
         check(L.tipb_neg_bitmap_build(ptr(_i64c(pos_edge_index)), ptr(self.range_dev), self.n_edges, num_nodes,
                                       self.n_rel, ptr(self.member), ptr(popcount), stream()), "neg_bitmap_build")
@@ -150,12 +157,12 @@ class _Membership(object):
         p_accept = float(num_nodes) ** 2 / float(1 << bits)
         need = max_index / p_accept
         self.n_new = int(need + Z_SIGMA * np.sqrt(need * (1.0 - p_accept) / p_accept + 1.0) + 4096)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._versions = (pos_edge_index._version, range_list._version)
 
 
 def _membership(pos_edge_index, num_nodes, range_list):
-    key = (pos_edge_index.data_ptr(), tuple(pos_edge_index.shape), pos_edge_index._version, range_list.data_ptr(),
-           tuple(range_list.shape), range_list._version, int(num_nodes), str(pos_edge_index.device))
+    key = (pos_edge_index.data_ptr(), tuple(pos_edge_index.shape), range_list.data_ptr(), tuple(range_list.shape),
+           int(num_nodes), str(pos_edge_index.device))
     m = _member_cache.get(key)
     if m is None:
         if len(_member_cache) > 16:
@@ -163,6 +170,8 @@ def _membership(pos_edge_index, num_nodes, range_list):
         m = _Membership(pos_edge_index, num_nodes, range_list)
         m._keepalive = (pos_edge_index, range_list)
         _member_cache[key] = m
+    elif m._versions != (pos_edge_index._version, range_list._version):
+        m.build(pos_edge_index, num_nodes, range_list)      # the positives were overwritten in place
     return m
 
 

@@ -105,25 +105,34 @@ def clear_plan_cache():
 
 
 def _tensor_key(t):
-    return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+    return None if t is None else (t.data_ptr(), tuple(t.shape), str(t.device))
+
+
+def _versions(*tensors):
+    return tuple(None if t is None else t._version for t in tensors)
 
 
 def cached_plan(edge_index, n_nodes, n_rel=1, edge_type=None, range_list=None, validate=True, **flags):
-    """Plans are cached per (edge tensors identity/version, flags): the reference's modules are
-    stateless but PyG's GCNConv(cached=True) keeps its normalised graph the same way."""
+    """Plans are cached per (edge tensors identity, flags): the reference's modules are stateless but PyG's
+    GCNConv(cached=True) keeps its normalised graph the same way.  If a key tensor was modified in place since
+    the plan was built (its version counter moved), the plan is rebuilt into the same buffers."""
     key = (_tensor_key(edge_index), _tensor_key(edge_type), _tensor_key(range_list), int(n_nodes), int(n_rel),
            tuple(sorted(flags.items())))
+    versions = _versions(edge_index, edge_type, range_list)
     plan = _plan_cache.get(key)
     if plan is None:
         if len(_plan_cache) > 64:
             _plan_cache.clear()
         plan = TypedCSR(edge_index.shape[1], n_nodes, n_rel, edge_index.device, **flags)
+        # keep the key tensors alive so that data_ptr() cannot be recycled under the cache
+        plan._keepalive = (edge_index, edge_type, range_list)
+        plan._versions = None
+        _plan_cache[key] = plan
+    if plan._versions != versions:
         plan.build(edge_index, edge_type, range_list)
         if validate:
             plan.check_status()
-        # keep the key tensors alive so that data_ptr() cannot be recycled under the cache
-        plan._keepalive = (edge_index, edge_type, range_list)
-        _plan_cache[key] = plan
+        plan._versions = versions
     return plan
 
 

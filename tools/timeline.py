@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 data, _ = bench.make_data("polypharmacy")
 torch.manual_seed(1111); ns.seed(1111, dev)
 model = layers.TIP(bench.settings_for("cat"), dev, mod="cat", data=data)
-opt = torch.optim.Adam(model.parameters(), lr=0.01, capturable=True)
+opt = torch.optim.Adam(model.parameters(), lr=0.01, capturable=True, fused=True)
 
 def ev(stream=None):
     e = torch.cuda.Event(enable_timing=True)
