@@ -159,21 +159,29 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
 }
 
 // d_z[n, :] (+)= sum_{s in node n} wacc_seg[s, :]
-__global__ void __launch_bounds__(128)
+// One CTA per node; NODE_REDUCE_THREADS / dim row groups, four rows in flight per group, fixed summation order.
+constexpr int NODE_REDUCE_THREADS = 512;
+__global__ void __launch_bounds__(NODE_REDUCE_THREADS)
 k_decoder_node_reduce(const int* __restrict__ node_ptr, const int* __restrict__ listing, const int* __restrict__ counts,
                       const float* __restrict__ wacc_seg, int dim, int accumulate, float* __restrict__ d_z) {
-    __shared__ float part[128];
+    __shared__ float part[NODE_REDUCE_THREADS];
     const int n = blockIdx.x;
     const int sb = node_ptr[n], se = node_ptr[n + 1];
     const bool listed = counts[TIPB_CSR_COUNT_REL_MAJOR] != 0;  // relation-major plan: node_ptr indexes the listing
-    const int per = 128 / dim;  // dim <= 128 and a power of two
+    const int per = NODE_REDUCE_THREADS / dim;  // dim <= 128 and a power of two
     const int k = threadIdx.x % dim, sg = threadIdx.x / dim;
-    float a = 0.f;
-    for (int i = sb + sg; i < se; i += per) {
-        const int s = listed ? listing[i] : i;
-        a += wacc_seg[int64_t(s) * dim + k];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = sb + sg;
+    for (; i + 3 * per < se; i += 4 * per) {
+        const int s0 = listed ? listing[i] : i, s1 = listed ? listing[i + per] : i + per;
+        const int s2 = listed ? listing[i + 2 * per] : i + 2 * per, s3 = listed ? listing[i + 3 * per] : i + 3 * per;
+        a0 += wacc_seg[int64_t(s0) * dim + k];
+        a1 += wacc_seg[int64_t(s1) * dim + k];
+        a2 += wacc_seg[int64_t(s2) * dim + k];
+        a3 += wacc_seg[int64_t(s3) * dim + k];
     }
-    part[threadIdx.x] = a;
+    for (; i < se; i += per) a0 += wacc_seg[int64_t(listed ? listing[i] : i) * dim + k];
+    part[threadIdx.x] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (threadIdx.x < dim) {
         float t = 0.f;
@@ -269,7 +277,7 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
     else if (mode == DEC_MODE_NEG) RUN(DEC_MODE_NEG)
     else RUN(DEC_MODE_GRAD)
 #undef RUN
-    k_decoder_node_reduce<<<(unsigned)v.n_nodes, 128, 0, s>>>(v.node_ptr, v.rel_seg, v.counts, acc_seg, dim, accumulate, d_z);
+    k_decoder_node_reduce<<<(unsigned)v.n_nodes, NODE_REDUCE_THREADS, 0, s>>>(v.node_ptr, v.rel_seg, v.counts, acc_seg, dim, accumulate, d_z);
     if (accumulate) {
         k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, zacc_seg, dim, 0.5f, dw_tmp);
         k_add_inplace<<<(unsigned)ceil_div(v.n_rel * dim, 256), 256, 0, s>>>(d_w, dw_tmp, v.n_rel * dim);

@@ -98,25 +98,74 @@ __global__ void __launch_bounds__(256) k_mt_generate(const uint32_t* __restrict_
     }
 }
 
-// word i of the window is a candidate iff it lies at or after the state's read position
-__global__ void k_accept_flags(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, int64_t n_words,
-                               uint32_t mask, uint32_t max_val, int* __restrict__ flags) {
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
-    uint32_t w = mt_temper(U[i]) & mask;
-    flags[i] = (i >= int64_t(*pos_ptr) && w <= max_val) ? 1 : 0;
+// Masked rejection as a stream compaction.  Word i of the window is a candidate iff it lies at or after the
+// state's read position; it is accepted iff (tempered & mask) <= max_val.  Two passes over the raw words, no flag
+// array: per-chunk counts -> scan of the (few thousand) chunk counts -> every chunk recomputes its flags and
+// writes its accepted values in word order.  Thread t of a chunk owns ACC_ITEMS consecutive words.
+constexpr int ACC_THREADS = 256;
+constexpr int ACC_ITEMS = 8;
+constexpr int ACC_CHUNK = ACC_THREADS * ACC_ITEMS;
+
+__device__ __forceinline__ unsigned accept_bits(const uint32_t* __restrict__ U, int64_t base, int64_t n_words,
+                                                int64_t first, uint32_t mask, uint32_t max_val, uint32_t* w) {
+    unsigned bits = 0;
+    if (base + ACC_ITEMS <= n_words) {
+        const uint4 q0 = *reinterpret_cast<const uint4*>(U + base), q1 = *reinterpret_cast<const uint4*>(U + base + 4);
+        w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w; w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < ACC_ITEMS; ++i) w[i] = base + i < n_words ? U[base + i] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int i = 0; i < ACC_ITEMS; ++i) {
+        w[i] = mt_temper(w[i]) & mask;
+        if (base + i < n_words && base + i >= first && w[i] <= max_val) bits |= 1u << i;
+    }
+    return bits;
 }
 
-__global__ void k_compact(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, int64_t n_words,
-                          uint32_t mask, uint32_t max_val, const int* __restrict__ slot, int* __restrict__ A,
-                          int* __restrict__ Apos) {
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
-    uint32_t w = mt_temper(U[i]) & mask;
-    if (i >= int64_t(*pos_ptr) && w <= max_val) {
-        int a = slot[i];
-        A[a] = int(w);
-        Apos[a] = int(i);
+__global__ void __launch_bounds__(ACC_THREADS)
+k_accept_count(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, int64_t n_words, uint32_t mask,
+               uint32_t max_val, int* __restrict__ chunk_cnt) {
+    __shared__ int sw[ACC_THREADS / 32];
+    uint32_t w[ACC_ITEMS];
+    const int64_t base = int64_t(blockIdx.x) * ACC_CHUNK + int64_t(threadIdx.x) * ACC_ITEMS;
+    int c = __popc(accept_bits(U, base, n_words, int64_t(*pos_ptr), mask, max_val, w));
+    c = warp_sum_i(c);
+    if (lane_id() == 0) sw[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < ACC_THREADS / 32; ++k) t += sw[k];
+        chunk_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(ACC_THREADS)
+k_compact(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, int64_t n_words, uint32_t mask,
+          uint32_t max_val, const int* __restrict__ chunk_off, int* __restrict__ A, int* __restrict__ Apos) {
+    __shared__ int sw[ACC_THREADS / 32];
+    uint32_t w[ACC_ITEMS];
+    const int64_t base = int64_t(blockIdx.x) * ACC_CHUNK + int64_t(threadIdx.x) * ACC_ITEMS;
+    const unsigned bits = accept_bits(U, base, n_words, int64_t(*pos_ptr), mask, max_val, w);
+    const int c = __popc(bits);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, o);
+        if (lane_id() >= o) incl += y;
+    }
+    if (lane_id() == 31) sw[warp_id()] = incl;
+    __syncthreads();
+    int a = chunk_off[blockIdx.x] + incl - c;
+    for (int k = 0; k < warp_id(); ++k) a += sw[k];
+#pragma unroll
+    for (int i = 0; i < ACC_ITEMS; ++i) {
+        if ((bits >> i) & 1u) {
+            A[a] = int(w[i]);
+            Apos[a] = int(base + i);
+            ++a;
+        }
     }
 }
 
@@ -298,6 +347,114 @@ k_chain_walk(const int64_t* __restrict__ table, const int* __restrict__ F, int n
         for (int q = r; q < n_rel; ++q) off[q] = -1;  // relations that could not be placed (r == n_rel: none)
         chain_out[0] = o;
     }
+}
+
+// Blocked form of the same walk.  The chain o_{r+1} = F_r[o_r - lo_r] is a composition of 861 table lookups, each
+// an L2 round trip when followed one after the other.  Cut the relations into blocks of CHAIN_BLOCK: stage 1
+// composes every block for ALL of its first relation's candidate offsets at once (one thread per candidate:
+// CHAIN_BLOCK dependent lookups, thousands of candidates in flight), stage 2 walks block to block
+// (n_rel / CHAIN_BLOCK lookups) and then lets one thread per block replay its block from the now known start to
+// emit off[].  Depth: 2 * CHAIN_BLOCK + n_rel / CHAIN_BLOCK lookups instead of n_rel.
+// G[f_off_{r0} + x] = offset of relation r0 + CHAIN_BLOCK if relation r0 starts at lo_{r0} + x; -1: out of words,
+// -2: left a bracket.
+constexpr int CHAIN_BLOCK = 30;
+constexpr int CHAIN_MAX_BLOCKS = 1024;
+
+struct ChainStep { int o; int fail; };
+// t = (lo, W, f_off, k) of one relation, staged in shared memory as four ints
+__device__ __forceinline__ ChainStep chain_advance(const int4 t, const int* __restrict__ F, int o) {
+    ChainStep st{o, 0};
+    if (t.w != 0) {
+        const int x = o - t.x;
+        if (x < 0 || x >= t.y) {
+            st.fail = NEG_STATUS_BRACKET_MISS;
+        } else {
+            const int nxt = F[t.z + x];
+            if (nxt < 0) st.fail = NEG_STATUS_OUT_OF_WORDS; else st.o = nxt;
+        }
+    }
+    return st;
+}
+__device__ __forceinline__ int4 chain_row(const int64_t* __restrict__ table, int r) {
+    const int64_t* tb = table + int64_t(r) * TAB;
+    return make_int4(int(tb[0]), int(tb[1]), int(tb[4]), int(tb[5]));
+}
+
+__global__ void __launch_bounds__(256)
+k_chain_blocks(const int64_t* __restrict__ table, const int* __restrict__ F, int n_rel, int* __restrict__ G) {
+    __shared__ int4 s_row[CHAIN_BLOCK];
+    const int r0 = blockIdx.y * CHAIN_BLOCK;
+    const int nr = min(CHAIN_BLOCK, n_rel - r0);
+    if (threadIdx.x < nr) s_row[threadIdx.x] = chain_row(table, r0 + threadIdx.x);
+    __syncthreads();
+    const int lo = s_row[0].x, W = s_row[0].y, f_off = s_row[0].z;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        int o = lo + x;
+        int res = 0;
+        for (int q = 0; q < nr; ++q) {
+            const ChainStep st = chain_advance(s_row[q], F, o);
+            if (st.fail) { res = st.fail == NEG_STATUS_OUT_OF_WORDS ? -1 : -2; break; }
+            o = st.o;
+        }
+        G[f_off + x] = res < 0 ? res : o;
+    }
+}
+
+__global__ void __launch_bounds__(CHAIN_MAX_BLOCKS)
+k_chain_stitch(const int64_t* __restrict__ table, const int* __restrict__ F, const int* __restrict__ G, int n_rel,
+               int* __restrict__ off, int* __restrict__ chain_out, int* __restrict__ status) {
+    extern __shared__ int4 s_tab4[];  // [n_rel]
+    __shared__ int s_start[CHAIN_MAX_BLOCKS + 1];
+    const int nb = (n_rel + CHAIN_BLOCK - 1) / CHAIN_BLOCK;
+    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) s_tab4[r] = chain_row(table, r);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        int b = 0;
+        for (; b < nb; ++b) {
+            s_start[b] = o;
+            const int4 t0 = s_tab4[b * CHAIN_BLOCK];
+            const int x = o - t0.x;
+            if (x < 0 || x >= t0.y) {
+                // a block whose first relation is empty never consults its bracket: replay it lookup by lookup
+                int oo = o, bad = 0;
+                for (int r = b * CHAIN_BLOCK; r < min((b + 1) * CHAIN_BLOCK, n_rel); ++r) {
+                    const ChainStep st = chain_advance(s_tab4[r], F, oo);
+                    if (st.fail) { bad = 1; break; }
+                    oo = st.o;
+                }
+                if (bad) { ++b; break; }
+                o = oo;
+                continue;
+            }
+            const int nxt = G[t0.z + x];
+            if (nxt < 0) { ++b; break; }
+            o = nxt;
+        }
+        for (int q = b; q < nb; ++q) s_start[q] = -1;  // blocks after a failure
+        s_start[nb] = o;
+    }
+    __syncthreads();
+    const int b = threadIdx.x;
+    if (b >= nb) return;
+    int o = s_start[b];
+    const int r0 = b * CHAIN_BLOCK, r1 = min(r0 + CHAIN_BLOCK, n_rel);
+    if (o < 0) {
+        for (int r = r0; r < r1; ++r) off[r] = -1;
+        return;
+    }
+    for (int r = r0; r < r1; ++r) {
+        const ChainStep st = chain_advance(s_tab4[r], F, o);
+        if (st.fail) {
+            atomicOr(status, st.fail);
+            for (int q = r; q < r1; ++q) off[q] = -1;
+            chain_out[0] = o;  // the last offset that could be placed
+            return;
+        }
+        off[r] = o;
+        o = st.o;
+    }
+    if (b == nb - 1) chain_out[0] = o;
 }
 
 // rounds 0 and 1, one thread per draw
@@ -530,7 +687,7 @@ k_bitmap_popcount(const uint32_t* __restrict__ member, int64_t words_per_rel, in
 static int64_t bitmap_words(int64_t n_nodes) { return (n_nodes * n_nodes + 31) / 32; }
 
 struct NegWs {
-    int *flags, *A, *Apos, *NHI, *PR, *F, *off, *chain_out;
+    int *flags, *A, *Apos, *NHI, *PR, *F, *G, *off, *chain_out;
     int *perm, *rounds, *round_ptr, *n_rounds;
     int round_cap;
     void* scan_ws;
@@ -545,6 +702,7 @@ static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t n_words, int
     t.NHI = c.take<int>(sum_l + 1);
     t.PR = c.take<int>(sum_l + 1);
     t.F = c.take<int>(sum_w + 1024);  // slack: the chain walk stages 2 KB windows with 16-byte copies
+    t.G = c.take<int>(sum_w + 1024);
     t.off = c.take<int>(n_rel + 1);
     t.chain_out = c.take<int>(4);
     t.perm = c.take<int>(n_edges + 1);
@@ -656,6 +814,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample: n_nodes must be in [2, 46340]");
     TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample: bad stream length");
     TIPB_CHECK_ARG(n_rel > 0 && n_rel * 20 <= 180 * 1024, "neg_sample: n_rel out of range");
+    TIPB_CHECK_ARG((reinterpret_cast<uintptr_t>(stream_words) & 15) == 0, "neg_sample: stream_words must be 16-byte aligned");
     TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
                    "neg_sample: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
@@ -669,11 +828,12 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     int rc;
 
     TIPB_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
-    k_accept_flags<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
-    if ((rc = exclusive_scan_i32(w.flags, w.flags, n_words, w.scan_ws, s))) return rc;
-    k_compact<<<(unsigned)ceil_div(n_words, T), T, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
-                                                           w.A, w.Apos);
-    const int* n_acc = w.flags + n_words;
+    const int64_t n_chunks = ceil_div(n_words, ACC_CHUNK);
+    k_accept_count<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
+    if ((rc = exclusive_scan_i32(w.flags, w.flags, n_chunks, w.scan_ws, s))) return rc;
+    k_compact<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
+                                                         w.A, w.Apos);
+    const int* n_acc = w.flags + n_chunks;
     if (exact_mode) {
         k_chain_exact<<<1, 1024, 0, s>>>(w.A, n_acc, member, wpr, range_list, (int)n_rel, w.round_cap, w.rounds,
                                          w.round_ptr, w.n_rounds, w.chain_out, status);
@@ -681,9 +841,17 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
     } else {
         k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
-        const size_t smem = size_t(n_rel) * 20 + size_t((WALK_AHEAD + 1) * WALK_WIN + 16) * sizeof(int);
-        if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
-        k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
+        const int n_blocks = int(ceil_div(n_rel, CHAIN_BLOCK));
+        if (n_blocks <= CHAIN_MAX_BLOCKS && size_t(n_rel) * sizeof(int4) <= 160 * 1024) {
+            const size_t tsm = size_t(n_rel) * sizeof(int4);
+            if ((rc = ensure_dyn_smem((const void*)k_chain_stitch, tsm))) return rc;
+            k_chain_blocks<<<dim3(16, (unsigned)n_blocks), T, 0, s>>>(table, w.F, (int)n_rel, w.G);
+            k_chain_stitch<<<1, CHAIN_MAX_BLOCKS, tsm, s>>>(table, w.F, w.G, (int)n_rel, w.off, w.chain_out, status);
+        } else {
+            const size_t smem = size_t(n_rel) * 20 + size_t((WALK_AHEAD + 1) * WALK_WIN + 16) * sizeof(int);
+            if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
+            k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
+        }
         if (n_edges > 0)
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,

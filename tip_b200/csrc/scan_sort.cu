@@ -145,18 +145,106 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunks(const int* in, int
     }
 }
 
-size_t scan_ws_bytes(int64_t n) { return size_t(ceil_div(n > 0 ? n : 1, SCAN_CHUNK)) * sizeof(int) + 256; }
+// Single-pass form (decoupled look-back): chunks are claimed in ticket order; a chunk publishes its aggregate,
+// then its warp 0 walks the published words of its predecessors 32 at a time until it meets an inclusive prefix,
+// and publishes its own.  Flag and value travel in ONE 64-bit word, so no fence is needed between them.
+//   state[c] = (flag << 32) | value,   flag 0: nothing yet, 1: chunk aggregate, 2: inclusive prefix
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lookback(const int* in, int* out, int64_t n, unsigned long long* __restrict__ state, int* __restrict__ ticket) {
+    __shared__ int sw[33];
+    __shared__ int s_chunk, s_excl;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    const int64_t base = int64_t(chunk) * SCAN_CHUNK + int64_t(threadIdx.x) * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int local = 0;
+    if (base + SCAN_ITEMS <= n) {
+        const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            const int4 q = p[i];
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = base + i < n ? in[base + i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) local += v[i];
+    int total;
+    const int ex = block_exclusive_scan(local, sw, &total);
+    if (warp_id() == 0) {
+        const int lane = lane_id();
+        volatile unsigned long long* vs = state;
+        int excl = 0;
+        if (chunk > 0) {
+            if (lane == 0) atomicExch(&state[chunk], (1ull << 32) | (unsigned)total);
+            int look = chunk - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long st = idx >= 0 ? vs[idx] : (2ull << 32);
+                while (__any_sync(FULL, (st >> 32) == 0)) {
+                    if ((st >> 32) == 0) st = vs[idx];
+                }
+                const unsigned pm = __ballot_sync(FULL, (st >> 32) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;   // nearest predecessor that already holds a prefix
+                int val = lane <= first ? int(unsigned(st)) : 0;
+                val = warp_sum_i(val);
+                excl += val;
+                if (pm) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            atomicExch(&state[chunk], (2ull << 32) | (unsigned)(excl + total));
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    int off = ex + s_excl;
+    if (base + SCAN_ITEMS <= n) {
+        int4* p = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            int4 q;
+            q.x = off; off += v[4 * i];
+            q.y = off; off += v[4 * i + 1];
+            q.z = off; off += v[4 * i + 2];
+            q.w = off; off += v[4 * i + 3];
+            p[i] = q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            if (base + i < n) out[base + i] = off;
+            off += v[i];
+        }
+    }
+    // one past the end receives the total
+    if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = s_excl + ex + local;
+}
+
+size_t scan_ws_bytes(int64_t n) { return size_t(ceil_div(n > 0 ? n : 1, SCAN_CHUNK) + 2) * sizeof(unsigned long long) + 256; }
 
 int exclusive_scan_i32(const int* in, int* out, int64_t n, void* ws, cudaStream_t s) {
-    int* sums = static_cast<int*>(ws);
     if (n <= 0) {
         TIPB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(int), s));
         return TIPB_OK;
     }
-    int64_t nb = ceil_div(n, SCAN_CHUNK);
-    k_scan_chunk_sums<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, sums);
-    k_scan_sums<<<1, 1024, 0, s>>>(sums, nb, out + n);
-    k_scan_chunks<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, out, n, sums);
+    const int64_t nb = ceil_div(n, SCAN_CHUNK);
+    unsigned long long* state = static_cast<unsigned long long*>(ws);
+    int* ticket = reinterpret_cast<int*>(state + nb);
+    TIPB_CHECK_CUDA(cudaMemsetAsync(ws, 0, size_t(nb + 1) * sizeof(unsigned long long), s));
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) {
+        // unaligned views: the three-launch form has no vector accesses
+        int* sums = reinterpret_cast<int*>(state);
+        k_scan_chunk_sums<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, sums);
+        k_scan_sums<<<1, 1024, 0, s>>>(sums, nb, out + n);
+        k_scan_chunks<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, out, n, sums);
+    } else {
+        k_scan_lookback<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, out, n, state, ticket);
+    }
     TIPB_CHECK_LAUNCH("exclusive_scan_i32");
     return TIPB_OK;
 }

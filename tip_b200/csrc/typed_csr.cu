@@ -189,19 +189,22 @@ __global__ void k_csr_pad(int64_t seg_cap, int n_nodes, int n_rel, int rel_major
     rvals[s] = uint32_t(s);
 }
 
-// degrees of a relation-major plan: a node's segments are reached through the secondary listing
-__global__ void k_csr_degrees_listed(int n_nodes, const int* __restrict__ node_ptr, const int* __restrict__ listing,
-                                     const int* __restrict__ seg_ptr, int* __restrict__ deg,
-                                     float* __restrict__ inv_deg) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
+// degrees of a relation-major plan: a node's segments are reached through the secondary listing (one warp per node)
+__global__ void __launch_bounds__(256)
+k_csr_degrees_listed(int n_nodes, const int* __restrict__ node_ptr, const int* __restrict__ listing,
+                     const int* __restrict__ seg_ptr, int* __restrict__ deg, float* __restrict__ inv_deg) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= n_nodes) return;
     int d = 0;
-    for (int i = node_ptr[n]; i < node_ptr[n + 1]; ++i) {
+    for (int i = node_ptr[n] + lane_id(); i < node_ptr[n + 1]; i += 32) {
         const int s = listing[i];
         d += seg_ptr[s + 1] - seg_ptr[s];
     }
-    deg[n] = d;
-    inv_deg[n] = 1.0f / float(d < 1 ? 1 : d);
+    d = warp_sum_i(d);
+    if (lane_id() == 0) {
+        deg[n] = d;
+        inv_deg[n] = 1.0f / float(d < 1 ? 1 : d);
+    }
 }
 
 // group_ptr[g] = first index i with sorted_keys[i] >= g, for g in [0, n_groups]
@@ -277,13 +280,29 @@ k_grp_count(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ 
     for (int n = threadIdx.x; n < 2 * n_nodes; n += blockDim.x) s_hist[n] = 0;
     __syncthreads();
     bool bad = false;
-    for (int64_t e = start + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < end; e += int64_t(gridDim.x) * blockDim.x) {
-        for (int dir = 0; dir <= doubled; ++dir) {
-            int node, other;
-            if (grp_entry(edge_index, E, e, dir != 0, by_src, drop_loops, n_nodes, n_other, node, other)) {
-                atomicAdd(&s_hist[node], 1);
-                if (dir == 0) atomicAdd(&s_hist[n_nodes + node], 1);
-            } else if (!(drop_loops && node == other)) {
+    // four independent pairs of 64-bit loads per thread and trip: the pass is a pure stream over the relation
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t e0 = start + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e0 < end; e0 += 4 * stride) {
+        int64_t ra[4], rb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t e = e0 + j * stride;
+            const int64_t ec = e < end ? e : end - 1;
+            ra[j] = edge_index[ec];
+            rb[j] = edge_index[E + ec];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e0 + j * stride >= end) break;
+            const int64_t nd = by_src ? ra[j] : rb[j], ot = by_src ? rb[j] : ra[j];
+            const bool in = nd >= 0 && nd < n_nodes && ot >= 0 && ot < n_other;
+            const bool loop = drop_loops && nd == ot;
+            if (in && !loop) {
+                atomicAdd(&s_hist[int(nd)], 1);
+                atomicAdd(&s_hist[n_nodes + int(nd)], 1);
+                // the reversed copy of a doubled plan lists the pair under its other endpoint
+                if (doubled) atomicAdd(&s_hist[int(ot)], 1);
+            } else if (!loop) {
                 bad = true;
             }
         }
@@ -394,10 +413,218 @@ k_grp_scatter(const int64_t* __restrict__ edge_index, const int64_t* __restrict_
     }
 }
 
-// dense key space -> compact segment table
+// ------------------------------------------------------------------------------------------------
+// Fast placement (node and other ids < 65535).  One CTA per (relation, direction), handed out largest relation
+// first (`order`), walks the relation in tiles of PLACE_TILE edges staged in shared memory as 16-bit ids:
+//   count    lanes holding the same node find each other with one ballot per key bit (__match_any_sync costs
+//            ~12 cycles per distinct value on sm_100a); warp w owns a contiguous run of the tile, so
+//            (warp, round, lane) order is input order; each entry keeps its rank inside its warp's run
+//   scan     per node: prefix over warps, then an exclusive scan over nodes -> the tile sorted by node, locally
+//   place    sorted_i[local position] = tile index (a shared-memory scatter)
+//   write    thread j writes local position j: consecutive threads write consecutive entries of a segment, so
+//            the global stores coalesce (a direct scatter touches one sector per entry).
+constexpr int PLACE_TILE = 2048;
+constexpr uint16_t PLACE_INVALID = 0xffffu;
+
+// order[rank] = relation, by decreasing size (ties by index): longest-processing-time-first over the CTAs
+__global__ void __launch_bounds__(256) k_rel_order(const int64_t* __restrict__ range_list, int n_rel,
+                                                   int* __restrict__ order) {
+    __shared__ int s_size[1024];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int mine = r < n_rel ? int(range_list[2 * r + 1] - range_list[2 * r]) : 0;
+    int rank = 0;
+    for (int q0 = 0; q0 < n_rel; q0 += 1024) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < 1024; q += blockDim.x)
+            s_size[q] = q0 + q < n_rel ? int(range_list[2 * (q0 + q) + 1] - range_list[2 * (q0 + q)]) : -1;
+        __syncthreads();
+        const int lim = min(1024, n_rel - q0);
+        for (int q = 0; q < lim; ++q) {
+            const int sz = s_size[q];
+            rank += (sz > mine || (sz == mine && q0 + q < r)) ? 1 : 0;
+        }
+    }
+    if (r < n_rel) order[rank] = r;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_grp_place(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list,
+            const int* __restrict__ order, int64_t E, int n_nodes, int n_other, int n_rel, int by_src, int drop_loops,
+            int rel_major, int doubled, int key_bits, const int* __restrict__ seg_start,
+            const int* __restrict__ cnt_fwd, int* __restrict__ eid, int* __restrict__ other_out) {
+    extern __shared__ int sm_i[];
+    constexpr int T = WARPS * 32;
+    int* cursor = sm_i;                                   // [n_nodes] absolute position of a node's next entry
+    int* delta = cursor + n_nodes;                        // [n_nodes] absolute - local position, this tile
+    int* lstart = delta + n_nodes;                        // [n_nodes] local position of a node's first entry
+    uint16_t* wh = reinterpret_cast<uint16_t*>(lstart + n_nodes);  // [WARPS][n_nodes]
+    uint16_t* cn = wh + ((WARPS * n_nodes + 1) & ~1);     // [TILE] node id (PLACE_INVALID: dropped entry)
+    uint16_t* co = cn + PLACE_TILE;                       // [TILE] other id
+    uint16_t* rk = co + PLACE_TILE;                       // [TILE] rank inside the warp's run
+    uint16_t* sorted_i = rk + PLACE_TILE;                 // [TILE] tile index by local position
+    __shared__ int s_scan[WARPS + 1];
+
+    const int dirs = doubled ? 2 : 1;
+    const int r = order[blockIdx.x / dirs], dir = blockIdx.x % dirs;
+    const int w = warp_id(), lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t start = range_list[2 * r], end = range_list[2 * r + 1];
+    for (int n = threadIdx.x; n < n_nodes; n += T) {
+        const int64_t key = seg_key(n, r, n_nodes, n_rel, rel_major);
+        cursor[n] = seg_start[key] + (dir ? cnt_fwd[key] : 0);
+    }
+    const bool node_is_a = (by_src != 0) != (dir != 0);  // column 0 (source) is this pass's node column
+    const int per = (n_nodes + T - 1) / T;               // nodes per thread in the scan phase
+    uint16_t* mywh = wh + w * n_nodes;
+    for (int64_t tile = start; tile < end; tile += PLACE_TILE) {
+        const int nt = int(end - tile < PLACE_TILE ? end - tile : PLACE_TILE);
+        __syncthreads();  // previous tile written out
+        for (int i0 = threadIdx.x; i0 < nt; i0 += 4 * T) {
+            int64_t ra[4], rb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * T;
+                const int64_t e = tile + (i < nt ? i : nt - 1);
+                ra[j] = edge_index[e];
+                rb[j] = edge_index[E + e];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * T;
+                if (i < nt) {
+                    const int64_t nd = node_is_a ? ra[j] : rb[j], ot = node_is_a ? rb[j] : ra[j];
+                    const bool ok = nd >= 0 && nd < n_nodes && ot >= 0 && ot < n_other && !(drop_loops && nd == ot);
+                    cn[i] = ok ? uint16_t(nd) : PLACE_INVALID;
+                    co[i] = uint16_t(ot);
+                }
+            }
+        }
+        for (int i = threadIdx.x; i < (WARPS * n_nodes + 1) / 2; i += T) reinterpret_cast<uint32_t*>(wh)[i] = 0u;
+        __syncthreads();
+        // ---- count
+        const int rounds = (((nt + WARPS - 1) / WARPS) + 31) >> 5;  // per warp
+        const int wbase = w * rounds * 32;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int i = wbase + rd * 32 + lane;
+            const uint16_t v = i < nt ? cn[i] : PLACE_INVALID;
+            const bool valid = v != PLACE_INVALID;
+            const int node = v;
+            unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                if (b < key_bits) {
+                    const bool bit = (node >> b) & 1;
+                    const unsigned m = __ballot_sync(FULL, bit);
+                    peers &= bit ? m : ~m;
+                }
+            }
+            int c0 = 0;
+            if (valid) c0 = mywh[node];
+            __syncwarp();
+            if (valid) {
+                const int rank = __popc(peers & lt);
+                if (rank == 0) mywh[node] = uint16_t(c0 + __popc(peers));
+                rk[i] = uint16_t(c0 + rank);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- scan: thread t owns nodes [t*per, (t+1)*per)
+        int mine = 0;
+        for (int j = 0; j < per; ++j) {
+            const int n = threadIdx.x * per + j;
+            if (n < n_nodes) {
+                int run = 0;
+#pragma unroll
+                for (int ww = 0; ww < WARPS; ++ww) {
+                    const int c = wh[ww * n_nodes + n];
+                    wh[ww * n_nodes + n] = uint16_t(run);
+                    run += c;
+                }
+                lstart[n] = run;  // the node's count for now
+                mine += run;
+            }
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_scan[w] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int ww = 0; ww < WARPS; ++ww) {
+                const int c = s_scan[ww];
+                s_scan[ww] = run;
+                run += c;
+            }
+            s_scan[WARPS] = run;
+        }
+        __syncthreads();
+        int ls = s_scan[w] + incl - mine;
+        for (int j = 0; j < per; ++j) {
+            const int n = threadIdx.x * per + j;
+            if (n < n_nodes) {
+                const int c = lstart[n];
+                lstart[n] = ls;
+                delta[n] = cursor[n] - ls;
+                cursor[n] += c;
+                ls += c;
+            }
+        }
+        const int n_valid = s_scan[WARPS];
+        __syncthreads();
+        // ---- place (shared memory)
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int i = wbase + rd * 32 + lane;
+            if (i < nt) {
+                const int node = cn[i];
+                if (node != PLACE_INVALID) sorted_i[lstart[node] + mywh[node] + rk[i]] = uint16_t(i);
+            }
+        }
+        __syncthreads();
+        // ---- write, coalesced
+        for (int j = threadIdx.x; j < n_valid; j += T) {
+            const int i = sorted_i[j];
+            const int pos = j + delta[cn[i]];
+            const int64_t e = tile + i;
+            eid[pos] = int(dir ? E + e : e);
+            other_out[pos] = int(co[i]);
+        }
+    }
+}
+
+static size_t place_smem(int warps, int64_t n_nodes) {
+    return size_t(3) * n_nodes * 4 + ((size_t(warps) * n_nodes + 1) & ~size_t(1)) * 2 + size_t(4) * PLACE_TILE * 2;
+}
+static int place_warps(int64_t n_nodes, int64_t n_other) {
+    if (n_nodes > 65534 || n_other > 65535) return 0;
+    if (place_smem(8, n_nodes) <= 200 * 1024) return 8;
+    if (place_smem(4, n_nodes) <= 200 * 1024) return 4;
+    return 0;
+}
+
+// dense key space -> compact segment table.  Keys are q = a * n_b + b with (a, b) = (relation, node) for
+// relation-major plans and (node, relation) for node-major ones.  The SECONDARY listing (the same segments grouped
+// by b) needs no sort either: scanning the non-empty flags in transposed key order (b * n_a + a) gives every
+// segment its position in that listing.
+__global__ void k_grp_flags(const int* __restrict__ cnt, int64_t n_keys, int n_a, int n_b, int* __restrict__ flags,
+                            int* __restrict__ flags_t) {
+    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= n_keys) return;
+    const int f = cnt[q] > 0 ? 1 : 0;
+    flags[q] = f;
+    const int64_t a = q / n_b, b = q % n_b;
+    flags_t[b * n_a + a] = f;
+}
+
 __global__ void k_grp_segments(const int* __restrict__ cnt, const int* __restrict__ seg_start,
-                               const int* __restrict__ seg_index, int64_t n_keys, int n_nodes, int n_rel, int rel_major,
-                               int* __restrict__ seg_ptr, int* __restrict__ seg_node, int* __restrict__ seg_rel,
+                               const int* __restrict__ seg_index, const int* __restrict__ pos_t, int64_t n_keys,
+                               int n_nodes, int n_rel, int rel_major, int* __restrict__ seg_ptr,
+                               int* __restrict__ seg_node, int* __restrict__ seg_rel, int* __restrict__ listing,
                                int* __restrict__ counts) {
     int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q > n_keys) return;
@@ -405,19 +632,35 @@ __global__ void k_grp_segments(const int* __restrict__ cnt, const int* __restric
         const int S = seg_index[n_keys];
         counts[TIPB_CSR_COUNT_SEGMENTS] = S;
         counts[TIPB_CSR_COUNT_VALID] = seg_start[n_keys];
+        counts[TIPB_CSR_COUNT_REL_MAJOR] = rel_major;
         seg_ptr[S] = seg_start[n_keys];
         return;
     }
     if (cnt[q] > 0) {
         const int s = seg_index[q];
         seg_ptr[s] = seg_start[q];
-        seg_unkey(uint32_t(q), n_nodes, n_rel, rel_major, seg_node[s], seg_rel[s]);
+        int node, rel;
+        seg_unkey(uint32_t(q), n_nodes, n_rel, rel_major, node, rel);
+        seg_node[s] = node;
+        seg_rel[s] = rel;
+        const int64_t tq = rel_major ? int64_t(node) * n_rel + rel : int64_t(rel) * n_nodes + node;
+        listing[pos_t[tq]] = s;
     }
 }
 
-__global__ void k_flag_positive(const int* __restrict__ cnt, int64_t n, int* __restrict__ flags) {
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = cnt[i] > 0 ? 1 : 0;
+// group pointers of both orders straight from the two scans, and the sentinel padding of the unused table tail
+__global__ void k_grp_tail(const int* __restrict__ seg_index, const int* __restrict__ pos_t, int64_t seg_cap, int n_a,
+                           int n_b, int n_nodes, int n_rel, int* __restrict__ ptr_a, int* __restrict__ ptr_b,
+                           int* __restrict__ seg_node, int* __restrict__ seg_rel, int* __restrict__ listing) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i <= n_a) ptr_a[i] = seg_index[i * n_b];
+    if (i <= n_b) ptr_b[i] = pos_t[i * n_a];
+    const int S = seg_index[int64_t(n_a) * n_b];
+    if (i >= S && i < seg_cap) {
+        seg_node[i] = n_nodes;
+        seg_rel[i] = n_rel;
+        listing[i] = int(i);
+    }
 }
 
 static int grp_warps(int64_t n_nodes) {
@@ -429,8 +672,10 @@ static int grp_warps(int64_t n_nodes) {
 }
 
 static bool use_grouped(const int64_t* edge_type, const int64_t* range_list, int64_t entries, int64_t n_nodes,
-                        int64_t n_rel) {
+                        int64_t n_other, int64_t n_rel, int doubled) {
+    // (a doubled plan lists every pair under both endpoints: one validity rule for both copies needs one id space)
     return range_list && !edge_type && entries > 0 && n_rel > 1 && n_rel <= 65535 && grp_warps(n_nodes) > 0 &&
+           (!doubled || n_nodes == n_other) &&
            n_nodes * n_rel <= 4 * entries + (int64_t(1) << 20);
 }
 
@@ -440,7 +685,7 @@ size_t csr_build_ws_bytes(int64_t entries, int64_t n_nodes, int64_t n_rel) {
     const int64_t dense = n_nodes * n_rel;
     if (dense <= 4 * entries + (int64_t(1) << 20) && dense > m) m = dense;  // grouped path scans the dense key space
     size_t arrays = 5 * (((m + 2) * 4 + 255) & ~size_t(255));
-    return arrays + sort_ws_bytes(m) + scan_ws_bytes(m + 2) + 1024;
+    return arrays + sort_ws_bytes(m) + scan_ws_bytes(m + 2) + size_t(n_rel + 64) * 4 + 2048;
 }
 
 int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t* range_list, int64_t E,
@@ -461,11 +706,12 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
     int* flags = c.take<int>(m + 2);
     void* sort_ws = c.take<char>(sort_ws_bytes(m));
     void* scan_ws = c.take<char>(scan_ws_bytes(m + 2));
+    int* order = c.take<int>(n_rel + 1);
 
     TIPB_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, 16 * sizeof(int), s));
     TIPB_CHECK_CUDA(cudaMemsetAsync(v.seg_ptr, 0, (v.seg_cap + 1) * sizeof(int), s));
     int rc;
-    if (use_grouped(edge_type, range_list, entries, n_nodes, n_rel)) {
+    if (use_grouped(edge_type, range_list, entries, n_nodes, n_other, n_rel, doubled)) {
         const int64_t n_keys = n_nodes * n_rel;
         int* cnt = reinterpret_cast<int*>(k0);
         int* seg_start = reinterpret_cast<int*>(v0);
@@ -482,12 +728,39 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
                                                                   rel_major, cnt, cnt_fwd, v.counts);
         }
         if ((rc = exclusive_scan_i32(cnt, seg_start, n_keys, scan_ws, s))) return rc;
-        k_flag_positive<<<(unsigned)ceil_div(n_keys, T), T, 0, s>>>(cnt, n_keys, seg_index);
+        const int n_a = int(rel_major ? n_rel : n_nodes), n_b = int(rel_major ? n_nodes : n_rel);
+        int* pos_t = reinterpret_cast<int*>(v1);
+        k_grp_flags<<<(unsigned)ceil_div(n_keys, T), T, 0, s>>>(cnt, n_keys, n_a, n_b, seg_index, pos_t);
         if ((rc = exclusive_scan_i32(seg_index, seg_index, n_keys, scan_ws, s))) return rc;
-        k_grp_segments<<<(unsigned)ceil_div(n_keys + 1, T), T, 0, s>>>(cnt, seg_start, seg_index, n_keys, (int)n_nodes,
-                                                                       (int)n_rel, rel_major, v.seg_ptr, v.seg_node,
-                                                                       v.seg_rel, v.counts);
-        const int warps = grp_warps(n_nodes);
+        if ((rc = exclusive_scan_i32(pos_t, pos_t, n_keys, scan_ws, s))) return rc;
+        k_grp_segments<<<(unsigned)ceil_div(n_keys + 1, T), T, 0, s>>>(cnt, seg_start, seg_index, pos_t, n_keys,
+                                                                       (int)n_nodes, (int)n_rel, rel_major, v.seg_ptr,
+                                                                       v.seg_node, v.seg_rel, v.rel_seg, v.counts);
+        {
+            int64_t span = v.seg_cap > n_a + 1 ? v.seg_cap : n_a + 1;
+            if (n_b + 1 > span) span = n_b + 1;
+            k_grp_tail<<<(unsigned)ceil_div(span, T), T, 0, s>>>(seg_index, pos_t, v.seg_cap, n_a, n_b, (int)n_nodes,
+                                                                 (int)n_rel, rel_major ? v.rel_seg_ptr : v.node_ptr,
+                                                                 rel_major ? v.node_ptr : v.rel_seg_ptr, v.seg_node,
+                                                                 v.seg_rel, v.rel_seg);
+        }
+        const int pw = place_warps(n_nodes, n_other);
+        if (pw) {
+            const size_t psm = place_smem(pw, n_nodes);
+            const int kb = bits_for(uint64_t(n_nodes - 1));
+            k_rel_order<<<(unsigned)ceil_div(n_rel, T), T, 0, s>>>(range_list, (int)n_rel, order);
+#define GRP_PLACE(WV)                                                                                               \
+            {                                                                                                       \
+                auto kern = k_grp_place<WV>;                                                                        \
+                if ((rc = ensure_dyn_smem((const void*)kern, psm))) return rc;                                      \
+                kern<<<(unsigned)(n_rel * (doubled ? 2 : 1)), WV * 32, psm, s>>>(                                   \
+                    edge_index, range_list, order, E, (int)n_nodes, (int)n_other, (int)n_rel, by_src, drop_loops,   \
+                    rel_major, doubled, kb, seg_start, cnt_fwd, v.eid, v.other);                                    \
+            }
+            if (pw == 8) GRP_PLACE(8) else GRP_PLACE(4)
+#undef GRP_PLACE
+        }
+        const int warps = pw ? 0 : grp_warps(n_nodes);
         const size_t smem = size_t(warps + 1) * n_nodes * sizeof(int);
 #define GRP_SCATTER(WV)                                                                                             \
         {                                                                                                           \
@@ -497,8 +770,15 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
                 edge_index, range_list, E, (int)n_nodes, (int)n_other, (int)n_rel, by_src, drop_loops, rel_major,   \
                 seg_start, cnt_fwd, v.eid, v.other);                                                                \
         }
-        if (warps == 8) GRP_SCATTER(8) else if (warps == 4) GRP_SCATTER(4) else GRP_SCATTER(2)
+        if (pw) {} else if (warps == 8) GRP_SCATTER(8) else if (warps == 4) GRP_SCATTER(4) else GRP_SCATTER(2)
 #undef GRP_SCATTER
+        const unsigned gn = (unsigned)ceil_div(n_nodes, T);
+        if (rel_major)
+            k_csr_degrees_listed<<<(unsigned)ceil_div(n_nodes * 32, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.rel_seg, v.seg_ptr, v.deg, v.inv_deg);
+        else
+            k_csr_degrees<<<gn, T, 0, s>>>((int)n_nodes, v.node_ptr, v.seg_ptr, v.deg, v.inv_deg);
+        TIPB_CHECK_LAUNCH("typed_csr_build (grouped)");
+        return TIPB_OK;
     } else if (entries > 0) {
         unsigned g = (unsigned)ceil_div(entries, T);
         k_csr_keys<<<g, T, 0, s>>>(edge_index, edge_type, range_list, E, entries, (int)n_nodes, (int)n_other,
@@ -520,7 +800,7 @@ int csr_build(const int64_t* edge_index, const int64_t* edge_type, const int64_t
         if ((rc = sort_pairs_u32(k0, v0, k1, v1, v.seg_cap, bits_for((uint64_t)n_nodes), sort_ws, s))) return rc;
         k_copy_u32_to_i32<<<gs, T, 0, s>>>(v1, v.rel_seg, v.seg_cap);
         k_group_ptr<uint32_t><<<gp, T, 0, s>>>(k1, v.seg_cap, (int)n_nodes, v.node_ptr);
-        k_csr_degrees_listed<<<(unsigned)ceil_div(n_nodes, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.rel_seg, v.seg_ptr,
+        k_csr_degrees_listed<<<(unsigned)ceil_div(n_nodes * 32, T), T, 0, s>>>((int)n_nodes, v.node_ptr, v.rel_seg, v.seg_ptr,
                                                                           v.deg, v.inv_deg);
     } else {
         k_group_ptr<int><<<gp, T, 0, s>>>(v.seg_node, v.seg_cap, (int)n_nodes, v.node_ptr);

@@ -376,11 +376,11 @@ class TIP(nn.Module):
                                                 check_status=check_status, out=self._neg_index)
             self._neg_plan.build(neg_index, range_list=d.dd_train_range)
         self.embeddings = self._encode()
-        cur.wait_stream(self._side)
         pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False,
                                    doubled=True, rel_major=True)
-        # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient
-        return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan)
+        # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient;
+        # only the negative pass waits for the side stream
+        return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan, neg_stream=self._side)
 
     def pred(self, dd_idx, dd_et):
         return self.decoder(self.embeddings, dd_idx, dd_et)

@@ -328,7 +328,7 @@ class _BCELossFunction(torch.autograd.Function):
     """loss = -mean(log(sig(pos)+eps)) - mean(log(1-sig(neg)+eps)); gradient computed in the forward pass."""
 
     @staticmethod
-    def forward(ctx, z, weight, plan_pos, plan_neg):
+    def forward(ctx, z, weight, plan_pos, plan_neg, neg_stream=None):
         z, weight = _f32c(z), _f32c(weight)
         n_nodes, dim = z.shape
         n_rel = weight.shape[0]
@@ -339,6 +339,9 @@ class _BCELossFunction(torch.autograd.Function):
                    L.tipb_decoder_workspace_bytes(plan_neg.n_edges, n_nodes, n_rel, dim))
         ws = workspace(need, z.device)
         for plan, sign, acc in ((plan_pos, 1, 0), (plan_neg, -1, 1)):
+            if acc and neg_stream is not None:
+                # the negative plan is built on a side stream; the positive pass above did not need it
+                torch.cuda.current_stream(z.device).wait_stream(neg_stream)
             check(L.tipb_decoder_bce_fused(ptr(plan.buf), plan.n_edges, n_nodes, n_rel, ptr(z), ptr(weight), dim, sign, acc,
                                            ptr(loss), ptr(d_z), ptr(d_w), ptr(ws), ws.numel(), stream()),
                   "decoder_bce_fused")
@@ -348,17 +351,17 @@ class _BCELossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         d_z, d_w = ctx.saved_tensors
-        return d_z * grad_loss, d_w * grad_loss, None, None
+        return d_z * grad_loss, d_w * grad_loss, None, None, None
 
 
-def bce_loss(z, weight, plan_pos, plan_neg):
+def bce_loss(z, weight, plan_pos, plan_neg, neg_stream=None):
     dim = z.shape[1]
     dp = _next_pow2(dim)
     if dp > 32:
         raise _lib.TipbError("decoder supports embedding widths up to 32")
     if dp != dim:
         z, weight = F.pad(z, (0, dp - dim)), F.pad(weight, (0, dp - dim))
-    return _BCELossFunction.apply(z, weight, plan_pos, plan_neg)
+    return _BCELossFunction.apply(z, weight, plan_pos, plan_neg, neg_stream)
 
 
 def decoder_sweep(z, weight, sigmoid=True):

@@ -152,10 +152,9 @@ class ShardedTIP(TIP):
             self._neg_local.copy_(neg_all[:, self.e_lo:self.e_hi])
             self._neg_plan_local.build(self._neg_local, range_list=self.local_range if self.n_local_rel else None)
         self.embeddings = self._encode()
-        cur.wait_stream(self._side)
         z = _ReduceBwd.apply(self.embeddings, self.coll)
         w = self.decoder.weight[self.r_lo:self.r_hi] if self.n_local_rel else self.decoder.weight[:1] * 0.0
-        local = ops.bce_loss(z, w, self.pos_plan, self._neg_plan_local)
+        local = ops.bce_loss(z, w, self.pos_plan, self._neg_plan_local, neg_stream=self._side)
         # local means -> share of the global means
         share = float(self.e_hi - self.e_lo) / float(max(d.dd_train_idx.shape[1], 1))
         return _ReduceFwd.apply(local * share, self.coll)

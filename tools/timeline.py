@@ -32,9 +32,8 @@ def step(marks=None):
         if marks is not None: marks["s_plan"] = ev()
     model.embeddings = model._encode()
     if marks is not None: marks["m_encoded"] = ev()
-    cur.wait_stream(model._side)
-    pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False, doubled=True)
-    loss = ops.bce_loss(model.embeddings, model.decoder.weight, pos_plan, model._neg_plan)
+    pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False, doubled=True, rel_major=True)
+    loss = ops.bce_loss(model.embeddings, model.decoder.weight, pos_plan, model._neg_plan, neg_stream=model._side)
     if marks is not None: marks["m_loss"] = ev()
     loss.backward()
     if marks is not None: marks["m_bwd"] = ev()
