@@ -176,6 +176,16 @@ int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream);
 int64_t tipb_mt19937_stream_words(int64_t n_new); /* rounds n_new up to the generator's granularity (454) */
 int tipb_mt19937_generate(const uint32_t* mt_state, uint32_t* stream_words /* [624 + n_new] */, int64_t n_new,
                           void* stream);
+/* The same stream produced by many CTAs (MT19937 jump-ahead, csrc/mt_jump.cu).  The stream after the key block is cut
+ * into chunks of chunk_words (a multiple of 454); chunk k >= 1 starts from the window x^(k*chunk_words) mod phi applied
+ * to the key block.  tipb_mt19937_jump_polys is HOST-ONLY (no CUDA call): polys_host[k-1] = that polynomial for
+ * k = 1..n_polys, 624 uint32 each (bit i of the polynomial = bit i%32 of word i/32); copy it to the device once.
+ * windows = device scratch of (n_chunks - 1) * 624 uint32.  Output identical to tipb_mt19937_generate. */
+int tipb_mt19937_jump_polys(int64_t chunk_words, int64_t n_polys, uint32_t* polys_host /* [n_polys*624] */);
+int64_t tipb_mt19937_chunk_count(int64_t n_new, int64_t chunk_words);
+int tipb_mt19937_generate_chunked(const uint32_t* mt_state, uint32_t* stream_words /* [624 + n_new] */, int64_t n_new,
+                                  int64_t chunk_words, const uint32_t* polys /* device */, int64_t n_polys,
+                                  uint32_t* windows, void* stream);
 size_t tipb_neg_bitmap_bytes(int64_t n_nodes, int64_t n_rel);
 int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges,
                           int64_t n_nodes, int64_t n_rel, uint32_t* member, int32_t* popcount /* [n_rel] */,

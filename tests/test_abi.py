@@ -73,6 +73,52 @@ def test_neg_table_build_is_host_only_and_consistent():
     assert np.all(lo <= start) and np.all(start <= lo + W)
 
 
+def test_mt19937_jump_polynomials_against_the_oracle_stream():
+    """tipb_mt19937_jump_polys (host only): g_k(T) applied to a key block by plain Horner == the window the
+    oracle's MT19937 reaches after k*chunk words (except the 31 unused low bits of word 0)."""
+    import ctypes as C
+
+    import numpy as np
+    from oracle import neg_sampling_oracle as nso
+    from tip_b200 import _lib
+    L = _lib.lib()
+    chunk, n_polys = 4540, 2
+    polys = np.zeros((n_polys, 624), dtype=np.uint32)
+    _lib.check(L.tipb_mt19937_jump_polys(chunk, n_polys, polys.ctypes.data_as(C.c_void_p)), "jump_polys")
+    assert L.tipb_mt19937_chunk_count(10 * chunk + 454, chunk) == 11
+    mt = nso.MT19937(1111)
+    w0 = np.asarray(mt.key, dtype=np.uint32).copy()
+
+    def advance(w):      # the one-word transition T on a 624-word window
+        y = (w[0] & np.uint32(0x80000000)) | (w[1] & np.uint32(0x7fffffff))
+        v = w[397] ^ (y >> np.uint32(1)) ^ (np.uint32(0x9908b0df) if (w[1] & np.uint32(1)) else np.uint32(0))
+        out = np.empty_like(w)
+        out[:-1] = w[1:]
+        out[-1] = v
+        return out
+
+    want, w = {}, w0.copy()
+    for n in range(1, n_polys * chunk + 1):
+        w = advance(w)
+        if n % chunk == 0:
+            want[n // chunk] = w.copy()
+    # the oracle's own generator agrees with `advance` (its key after one refill = the window 624 words on)
+    mt._twist()
+    w624 = w0.copy()
+    for _ in range(624):
+        w624 = advance(w624)
+    assert np.array_equal(np.asarray(mt.key, dtype=np.uint32), w624)
+    for k in range(1, n_polys + 1):
+        bits = np.unpackbits(polys[k - 1].view(np.uint8), bitorder="little")
+        assert not bits[19937:].any()
+        h = np.zeros(624, dtype=np.uint32)
+        for i in range(19936, -1, -1):
+            h = advance(h)
+            if bits[i]:
+                h ^= w0
+        assert np.array_equal(h[1:], want[k][1:]) and (h[0] >> 31) == (want[k][0] >> 31), k
+
+
 def test_argument_errors_are_reported_not_thrown():
     from tip_b200 import _lib
     L = _lib.lib()

@@ -274,6 +274,45 @@ def test_negative_sampling_bit_exact(golden_neg):
         assert np.array_equal(st[1], g["key_end"]) and st[2] == int(g["pos_end"]), case + " final MT state"
 
 
+def test_mt19937_chunked_generation_equals_serial():
+    """csrc/mt_jump.cu: the stream produced by one CTA per chunk (jump-ahead) == the serial recurrence == numpy"""
+    import ctypes as C
+    from tip_b200 import _lib
+    L = _lib.lib()
+    d = dev()
+    rs = np.random.RandomState(77)
+    key = rs.get_state()[1].astype(np.uint32)
+    state = T(np.concatenate([key, [624]]).astype(np.uint32).view(np.int32), d)
+    for chunk, n_new in ((454 * 2, 454 * 2), (454 * 368, 454 * 368 * 3), (454 * 4, 454 * 4 * 9 + 454)):
+        n_chunks = int(L.tipb_mt19937_chunk_count(n_new, chunk))
+        n_polys = max(n_chunks - 1, 1)
+        host = np.zeros((n_polys, 624), dtype=np.uint32)
+        _lib.check(L.tipb_mt19937_jump_polys(chunk, n_polys, host.ctypes.data_as(C.c_void_p)), "polys")
+        polys = T(host.view(np.int32), d)
+        windows = torch.zeros((n_polys, 624), dtype=torch.int32, device=d)
+        serial = torch.zeros(624 + n_new, dtype=torch.int32, device=d)
+        par = torch.zeros(624 + n_new, dtype=torch.int32, device=d)
+        _lib.check(L.tipb_mt19937_generate(_lib.ptr(state), _lib.ptr(serial), n_new, _lib.stream()), "serial")
+        _lib.check(L.tipb_mt19937_generate_chunked(_lib.ptr(state), _lib.ptr(par), n_new, chunk, _lib.ptr(polys), n_polys,
+                                                   _lib.ptr(windows), _lib.stream()), "chunked")
+        assert torch.equal(serial, par), (chunk, n_new)
+        if n_chunks > 1:     # the jumped windows are stream words themselves (bar the unused low bits of word 0)
+            w = windows[:n_chunks - 1].cpu().numpy().view(np.uint32)
+            ref = serial.cpu().numpy().view(np.uint32)
+            for k in range(1, n_chunks):
+                assert np.array_equal(w[k - 1][1:], ref[k * chunk + 1:k * chunk + 624])
+                assert (w[k - 1][0] >> 31) == (ref[k * chunk] >> 31)
+    # and numpy: tempered words of the stream after the key block == RandomState(77).randint stream
+    raw = par.cpu().numpy().view(np.uint32)[624:624 + 2000].astype(np.uint64)
+    y = raw ^ (raw >> 11)
+    y ^= (y << 7) & 0x9d2c5680
+    y ^= (y << 15) & 0xefc60000
+    y ^= y >> 18
+    gen = np.random.MT19937()
+    gen.state = {"bit_generator": "MT19937", "state": {"key": key, "pos": 624}}
+    assert np.array_equal((y & 0xffffffff).astype(np.uint32), gen.random_raw(2000).astype(np.uint32))
+
+
 def test_negative_sampling_seed_and_numpy_handover():
     from oracle import neg_sampling_oracle as nso
     from tip_b200 import neg_sampling as ns

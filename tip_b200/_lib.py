@@ -49,6 +49,9 @@ SIGNATURES = {
     "tipb_mt19937_seed": (C.c_int, [_p, _u32, _p]),
     "tipb_mt19937_stream_words": (_i64, [_i64]),
     "tipb_mt19937_generate": (C.c_int, [_p, _p, _i64, _p]),
+    "tipb_mt19937_jump_polys": (C.c_int, [_i64, _i64, _p]),
+    "tipb_mt19937_chunk_count": (_i64, [_i64, _i64]),
+    "tipb_mt19937_generate_chunked": (C.c_int, [_p, _p, _i64, _i64, _p, _i64, _p, _p]),
 }
 
 CSR_FIELDS = ("counts", "eid", "other", "seg_ptr", "seg_node", "seg_rel", "node_ptr", "deg", "inv_deg",

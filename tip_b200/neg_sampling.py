@@ -26,6 +26,8 @@ Z_SIGMA = 7.0          # half-width of the offset brackets, in standard deviatio
 _member_cache = {}     # positive-pair bitmaps + bracket tables, keyed on the identity of (pos_edge_index, range_list)
 _rng = {}              # device index -> _DeviceRng
 _prefetch = True
+_chunked = True        # generate the MT19937 stream with one CTA per CHUNK words (csrc/mt_jump.cu)
+CHUNK = 454 * 368      # words per CTA: 64 chunks for the 10.6 M words of a polypharmacy-shape step
 
 
 class _DeviceRng(object):
@@ -38,6 +40,8 @@ class _DeviceRng(object):
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self.ready = None       # event: the prefetch on `side` has finished
         self.forked = False     # a prefetch is in flight that the caller's stream has not joined yet
+        self.polys = None       # jump-ahead polynomials [n, 624] and the chunk start windows they produce
+        self.windows = None
         with torch.cuda.device(device):
             check(lib().tipb_mt19937_seed(ptr(self.state), 1111, stream()), "mt19937_seed")   # src/layers.py:14
 
@@ -51,14 +55,32 @@ class _DeviceRng(object):
         self.join()
         self.valid = False
 
+    def _jump_polys(self, n_polys):
+        """jump polynomials x^(k*CHUNK) mod phi, k = 1..n_polys, on the device (host computation, once)"""
+        if self.polys is None or self.polys.shape[0] < n_polys:
+            n_polys = max(n_polys, 2 * (0 if self.polys is None else self.polys.shape[0]))
+            host = np.zeros((n_polys, 624), dtype=np.uint32)
+            check(lib().tipb_mt19937_jump_polys(CHUNK, n_polys, host.ctypes.data_as(C.c_void_p)), "mt19937_jump_polys")
+            self.join()
+            self.polys = torch.from_numpy(host.view(np.int32)).to(self.device)
+            self.windows = torch.empty((n_polys, 624), dtype=torch.int32, device=self.device)
+        return self.polys
+
     def generate(self, n_new):
+        """624 + n_new untempered words from the current state: CHUNK-word pieces on one CTA each (jump-ahead)"""
         L = lib()
         n_new = int(L.tipb_mt19937_stream_words(int(n_new)))
         if self.words is None or self.n_new < n_new:
             self.join()
             self.words = torch.empty(624 + n_new, dtype=torch.int32, device=self.device)
             self.n_new = n_new
-        check(L.tipb_mt19937_generate(ptr(self.state), ptr(self.words), self.n_new, stream()), "mt19937_generate")
+        n_chunks = int(L.tipb_mt19937_chunk_count(self.n_new, CHUNK))
+        if not _chunked or n_chunks <= 1:
+            check(L.tipb_mt19937_generate(ptr(self.state), ptr(self.words), self.n_new, stream()), "mt19937_generate")
+            return
+        polys = self._jump_polys(n_chunks - 1)
+        check(L.tipb_mt19937_generate_chunked(ptr(self.state), ptr(self.words), self.n_new, CHUNK, ptr(polys),
+                                              polys.shape[0], ptr(self.windows), stream()), "mt19937_generate_chunked")
 
 
 def _device_of(device=None):
