@@ -152,6 +152,17 @@ int tipb_decoder_bwd(const void* plan_doubled, int64_t n_edges, int64_t n_nodes,
 int tipb_decoder_bce_fused(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
                            const float* weight, int dim, int sign, int accumulate, float* loss_out, float* d_z,
                            float* d_weight, void* ws, size_t ws_bytes, void* stream);
+/* The same loss term for a MIRRORED edge set -- the layout to_bidirection/process_edges produce (src/utils.py:17-23):
+ * every relation range holds its pairs and then the same pairs with rows swapped.  Every (node, relation) segment of
+ * the doubled plan would then list each neighbour twice, so the by-target plan (one listing per directed edge, the
+ * plan the R-GCN forward already has) is enough: half the gather work, same result up to summation order.
+ * tipb_edges_mirrored sets flag_out[0] = 1 iff edge_index/range_list have that layout. */
+int tipb_decoder_bce_fused_mirrored(const void* plan_by_target, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                                    const float* z, const float* weight, int dim, int sign, int accumulate,
+                                    float* loss_out, float* d_z, float* d_weight, void* ws, size_t ws_bytes,
+                                    void* stream);
+int tipb_edges_mirrored(const int64_t* edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_rel,
+                        int32_t* flag_out, void* stream);
 /* all n_nodes^2 x n_rel scores (BASELINE.json config 5): out[r,i,j] */
 int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim,
                        int apply_sigmoid, float* out, void* stream);

@@ -482,3 +482,49 @@ def test_bce_loss_against_oracle():
     et2 = torch.zeros(2, dtype=torch.long)
     l_ref = to.tip_loss(to.decoder(zs, T(e2), et2, ws), to.decoder(zs, T(e2), et2, ws))
     close(l_gpu, l_ref, rtol=1e-6, what="saturated loss")
+
+
+def test_bce_loss_mirrored_edge_set_uses_the_by_target_plan():
+    """process_edges output is mirrored (src/utils.py:17-23): the positive pass then runs over the R-GCN's by-target
+    plan (one listing per directed edge) and must give the doubled-plan / oracle result."""
+    from oracle import tip_oracle as to
+    from tip_b200 import ops
+    d = dev()
+    rng = np.random.default_rng(11)
+    n, r, dim = 300, 40, 16
+    halves, rl, et = [], [], []
+    start = 0
+    for rel in range(r):
+        k = int(rng.integers(0, 900)) if rel != 7 else 0          # one empty relation
+        pairs = rng.integers(0, n, (2, k)).astype(np.int64)
+        halves.append(np.concatenate([pairs, pairs[::-1]], axis=1))
+        rl.append([start, start + 2 * k])
+        et.append(np.full(2 * k, rel, dtype=np.int64))
+        start += 2 * k
+    ei, rl, et = np.concatenate(halves, axis=1), np.array(rl, dtype=np.int64), np.concatenate(et)
+    e = ei.shape[1]
+    ei_t, rl_t = T(ei, d), T(rl, d)
+    assert ops.edges_mirrored(ei_t, rl_t)
+    broken = ei_t.clone()
+    broken[0, e // 2] = (broken[0, e // 2] + 1) % n
+    assert not ops.edges_mirrored(broken, rl_t)
+    assert not ops.edges_mirrored(ei_t[:, :-2].contiguous(), rl_t)        # ranges do not tile the edges
+    neg = rng.integers(0, n, (2, e)).astype(np.int64)
+    torch.manual_seed(5)
+    z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
+    plan_neg = ops.TypedCSR(e, n, r, d, doubled=True).build(T(neg, d), range_list=rl_t)
+    results = []
+    for plan_pos in (ops.positive_decoder_plan(ei_t, n, r, rl_t),
+                     ops.TypedCSR(e, n, r, d, doubled=True, rel_major=True).build(ei_t, range_list=rl_t)):
+        zg, wg = z.to(d).requires_grad_(True), w.to(d).requires_grad_(True)
+        loss = ops.bce_loss(zg, wg, plan_pos, plan_neg)
+        loss.backward()
+        results.append((loss.detach(), zg.grad, wg.grad))
+    assert not ops.positive_decoder_plan(ei_t, n, r, rl_t).doubled
+    z64, w64 = z.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = to.tip_loss(to.decoder(z64, T(ei), T(et), w64), to.decoder(z64, T(neg), T(et), w64))
+    ref.backward()
+    for loss, dz, dw in results:
+        close(loss, ref, rtol=1e-5, what="loss")
+        close(dz, z64.grad, what="dz")
+        close(dw, w64.grad, what="dw")

@@ -243,6 +243,25 @@ k_decoder_sweep(const float* __restrict__ z, const float* __restrict__ w, int n_
     }
 }
 
+// the layout src/utils.py:17-23 (to_bidirection) produces: every relation range is [pairs..., the same pairs with
+// rows swapped...]; flag stays 1 iff that holds for every relation (and the ranges tile [0, n_edges))
+__global__ void k_mirror_init(int* flag) { *flag = 1; }
+__global__ void __launch_bounds__(256)
+k_mirror_check(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ range_list, int64_t n_edges,
+               int* __restrict__ flag) {
+    const int r = blockIdx.x;
+    const int64_t beg = range_list[2 * r], end = range_list[2 * r + 1];
+    const int64_t prev_end = r == 0 ? 0 : range_list[2 * r - 1];
+    bool ok = beg == prev_end && end >= beg && end <= n_edges && ((end - beg) & 1) == 0;
+    if (r == int(gridDim.x) - 1) ok = ok && end == n_edges;
+    if (ok) {
+        const int64_t half = (end - beg) >> 1;
+        for (int64_t e = beg + threadIdx.x; e < beg + half; e += 256)
+            ok = ok && edge_index[e] == edge_index[n_edges + e + half] && edge_index[n_edges + e] == edge_index[e + half];
+    }
+    if (!ok) atomicAnd(flag, 0);
+}
+
 static int dec_seg_grid() { return sm_count() * 2; }
 
 struct DecWs { float *acc_seg, *zacc_seg, *loss_part, *dw_tmp; };
@@ -252,7 +271,7 @@ static size_t dec_ws_bytes(int64_t seg_cap, int64_t n_rel, int dim) {
 
 template <int LPR>
 static int decoder_seg_run(const CsrView& v, int mode, const float* z, const float* w, const float* grad_out,
-                           int64_t n_edges, int apply_sigmoid, int accumulate, float* loss_out, float* d_z,
+                           int64_t n_edges, int apply_sigmoid, int accumulate, int mult, float* loss_out, float* d_z,
                            float* d_w, void* ws, cudaStream_t s) {
     const int dim = LPR * 4;
     Carver c(ws);
@@ -263,7 +282,9 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
     float* loss_part = c.take<float>(n_warps);
     float* dw_tmp = c.take<float>(size_t(v.n_rel) * dim);
     const size_t smem = size_t(v.n_nodes) * dim * sizeof(float);
-    const float inv_count = n_edges > 0 ? 1.0f / float(n_edges) : 0.f;
+    // mult = 1: doubled plan (every pair listed under both endpoints); mult = 2: one listing per directed edge of a
+    // mirrored edge set (each (node, relation) segment of the doubled plan would hold every neighbour twice)
+    const float inv_count = n_edges > 0 ? float(mult) / float(n_edges) : 0.f;
     int rc;
 #define RUN(MODEV)                                                                                                  \
     {                                                                                                               \
@@ -285,24 +306,24 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
         k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, zacc_seg, dim, 0.5f, d_w);
     }
     if (mode != DEC_MODE_GRAD)
-        k_loss_reduce<<<1, 1024, 0, s>>>(loss_part, n_warps, 0.5f * inv_count, accumulate, loss_out);
+        k_loss_reduce<<<1, 1024, 0, s>>>(loss_part, n_warps, 0.5f * inv_count, accumulate, loss_out);  // inv_count has mult
     TIPB_CHECK_LAUNCH("decoder_seg");
     return TIPB_OK;
 }
 
 static int decoder_seg_dispatch(const void* plan, int mode, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
                                 const float* z, const float* w, const float* grad_out, int dim, int apply_sigmoid,
-                                int accumulate, float* loss_out, float* d_z, float* d_w, void* ws, size_t ws_bytes,
-                                cudaStream_t s) {
-    CsrView v = csr_view(plan, 2 * n_edges, n_nodes, n_rel);
+                                int accumulate, int mult, float* loss_out, float* d_z, float* d_w, void* ws,
+                                size_t ws_bytes, cudaStream_t s) {
+    CsrView v = csr_view(plan, mult == 2 ? n_edges : 2 * n_edges, n_nodes, n_rel);
     TIPB_CHECK_ARG(ws_bytes >= dec_ws_bytes(v.seg_cap, n_rel, dim), "decoder: workspace too small");
     TIPB_CHECK_ARG(size_t(n_nodes) * dim * 4 + 1024 <= size_t(max_smem_optin()),
                    "decoder: z (%lld x %d) does not fit in shared memory", (long long)n_nodes, dim);
     switch (dim) {
-        case 4: return decoder_seg_run<1>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
-        case 8: return decoder_seg_run<2>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
-        case 16: return decoder_seg_run<4>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
-        case 32: return decoder_seg_run<8>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, loss_out, d_z, d_w, ws, s);
+        case 4: return decoder_seg_run<1>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);
+        case 8: return decoder_seg_run<2>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);
+        case 16: return decoder_seg_run<4>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);
+        case 32: return decoder_seg_run<8>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);
     }
     set_last_error("decoder: dim=%d not in {4,8,16,32} (the Python layer pads)", dim);
     return TIPB_ERR_UNSUPPORTED;
@@ -352,7 +373,7 @@ int tipb_decoder_bwd(const void* plan_doubled, int64_t n_edges, int64_t n_nodes,
                      float* d_weight, void* ws, size_t ws_bytes, void* stream) {
     TIPB_CHECK_ARG(plan_doubled && z && weight && grad_out && d_z && d_weight && ws, "decoder_bwd: NULL argument");
     return decoder_seg_dispatch(plan_doubled, DEC_MODE_GRAD, n_edges, n_nodes, n_rel, z, weight, grad_out, dim,
-                                apply_sigmoid, 0, nullptr, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
+                                apply_sigmoid, 0, 1, nullptr, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int tipb_decoder_bce_fused(const void* plan_doubled, int64_t n_edges, int64_t n_nodes, int64_t n_rel, const float* z,
@@ -361,7 +382,30 @@ int tipb_decoder_bce_fused(const void* plan_doubled, int64_t n_edges, int64_t n_
     TIPB_CHECK_ARG(plan_doubled && z && weight && loss_out && d_z && d_weight && ws, "decoder_bce_fused: NULL argument");
     TIPB_CHECK_ARG(sign == 1 || sign == -1, "decoder_bce_fused: sign must be +1 (positives) or -1 (negatives)");
     return decoder_seg_dispatch(plan_doubled, sign > 0 ? DEC_MODE_POS : DEC_MODE_NEG, n_edges, n_nodes, n_rel, z, weight,
-                                nullptr, dim, 1, accumulate, loss_out, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
+                                nullptr, dim, 1, accumulate, 1, loss_out, d_z, d_weight, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int tipb_decoder_bce_fused_mirrored(const void* plan_by_target, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                                    const float* z, const float* weight, int dim, int sign, int accumulate,
+                                    float* loss_out, float* d_z, float* d_weight, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    TIPB_CHECK_ARG(plan_by_target && z && weight && loss_out && d_z && d_weight && ws,
+                   "decoder_bce_fused_mirrored: NULL argument");
+    TIPB_CHECK_ARG(sign == 1 || sign == -1, "decoder_bce_fused_mirrored: sign must be +1 or -1");
+    return decoder_seg_dispatch(plan_by_target, sign > 0 ? DEC_MODE_POS : DEC_MODE_NEG, n_edges, n_nodes, n_rel, z, weight,
+                                nullptr, dim, 1, accumulate, 2, loss_out, d_z, d_weight, ws, ws_bytes,
+                                (cudaStream_t)stream);
+}
+
+int tipb_edges_mirrored(const int64_t* edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_rel,
+                        int32_t* flag_out, void* stream) {
+    TIPB_CHECK_ARG(edge_index && range_list && flag_out, "edges_mirrored: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_mirror_init<<<1, 1, 0, s>>>(flag_out);
+    if (n_rel > 0)
+        k_mirror_check<<<(unsigned)n_rel, 256, 0, s>>>(edge_index, range_list, n_edges, flag_out);
+    TIPB_CHECK_LAUNCH("edges_mirrored");
+    return TIPB_OK;
 }
 
 int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid,

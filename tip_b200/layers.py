@@ -367,7 +367,7 @@ class TIP(nn.Module):
             self._neg_index = torch.empty_like(d.dd_train_idx)
             self._neg_plan = ops.TypedCSR(d.dd_train_idx.shape[1], d.n_drug, d.n_dd_et, self.device, by_src=False,
                                           doubled=True, rel_major=True)
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # sampler -> plan is the critical chain
         # the negatives do not depend on the encoder: sample and index them on a side stream meanwhile
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)
@@ -376,8 +376,7 @@ class TIP(nn.Module):
                                                 check_status=check_status, out=self._neg_index)
             self._neg_plan.build(neg_index, range_list=d.dd_train_range)
         self.embeddings = self._encode()
-        pos_plan = ops.cached_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, range_list=d.dd_train_range, by_src=False,
-                                   doubled=True, rel_major=True)
+        pos_plan = ops.positive_decoder_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, d.dd_train_range)
         # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient;
         # only the negative pass waits for the side stream
         return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan, neg_stream=self._side)

@@ -37,7 +37,7 @@ class _DeviceRng(object):
         self.words = None       # untempered stream generated from `state` (624 + n_new words)
         self.n_new = 0
         self.valid = False      # `words` matches the current state
-        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.side = torch.cuda.Stream(device=device)      # next step's words: lowest priority, nobody waits for it
         self.ready = None       # event: the prefetch on `side` has finished
         self.forked = False     # a prefetch is in flight that the caller's stream has not joined yet
         self.polys = None       # jump-ahead polynomials [n, 624] and the chunk start windows they produce

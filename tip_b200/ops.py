@@ -338,13 +338,14 @@ class _BCELossFunction(torch.autograd.Function):
         need = max(L.tipb_decoder_workspace_bytes(plan_pos.n_edges, n_nodes, n_rel, dim),
                    L.tipb_decoder_workspace_bytes(plan_neg.n_edges, n_nodes, n_rel, dim))
         ws = workspace(need, z.device)
-        for plan, sign, acc in ((plan_pos, 1, 0), (plan_neg, -1, 1)):
-            if acc and neg_stream is not None:
+        for acc, (plan, sign) in enumerate(((plan_pos, 1), (plan_neg, -1))):
+            if sign < 0 and neg_stream is not None:
                 # the negative plan is built on a side stream; the positive pass above did not need it
                 torch.cuda.current_stream(z.device).wait_stream(neg_stream)
-            check(L.tipb_decoder_bce_fused(ptr(plan.buf), plan.n_edges, n_nodes, n_rel, ptr(z), ptr(weight), dim, sign, acc,
-                                           ptr(loss), ptr(d_z), ptr(d_w), ptr(ws), ws.numel(), stream()),
-                  "decoder_bce_fused")
+            # a by-target plan (one listing per directed edge) is only ever passed for a mirrored edge set
+            fused = L.tipb_decoder_bce_fused if plan.doubled else L.tipb_decoder_bce_fused_mirrored
+            check(fused(ptr(plan.buf), plan.n_edges, n_nodes, n_rel, ptr(z), ptr(weight), dim, sign, acc,
+                        ptr(loss), ptr(d_z), ptr(d_w), ptr(ws), ws.numel(), stream()), "decoder_bce_fused")
         ctx.save_for_backward(d_z, d_w)
         return loss.reshape(())
 
@@ -352,6 +353,34 @@ class _BCELossFunction(torch.autograd.Function):
     def backward(ctx, grad_loss):
         d_z, d_w = ctx.saved_tensors
         return d_z * grad_loss, d_w * grad_loss, None, None, None
+
+
+_mirror_cache = {}
+
+
+def edges_mirrored(edge_index, range_list):
+    """True iff every relation range is [pairs..., the same pairs with rows swapped...] (src/utils.py:17-23).
+    Checked on the device once per (tensor, version); one host synchronisation at that time."""
+    key = (_tensor_key(edge_index), _tensor_key(range_list))
+    versions = _versions(edge_index, range_list)
+    hit = _mirror_cache.get(key)
+    if hit is None or hit[0] != versions:
+        if len(_mirror_cache) > 64:
+            _mirror_cache.clear()
+        flag = torch.zeros(1, dtype=torch.int32, device=edge_index.device)
+        rl = _i64c(range_list.to(torch.long))
+        check(lib().tipb_edges_mirrored(ptr(_i64c(edge_index)), ptr(rl), edge_index.shape[1], rl.shape[0], ptr(flag),
+                                        stream()), "edges_mirrored")
+        hit = _mirror_cache[key] = (versions, bool(int(flag.item())), (edge_index, range_list))
+    return hit[1]
+
+
+def positive_decoder_plan(edge_index, n_nodes, n_rel, range_list):
+    """index structure for the positive pass of bce_loss: the R-GCN's own by-target plan when the edge set is
+    mirrored (always the case for process_edges output), else the doubled relation-major plan"""
+    if edges_mirrored(edge_index, range_list):
+        return cached_plan(edge_index, n_nodes, n_rel, by_src=False, edge_type=None, range_list=range_list)
+    return cached_plan(edge_index, n_nodes, n_rel, range_list=range_list, by_src=False, doubled=True, rel_major=True)
 
 
 def bce_loss(z, weight, plan_pos, plan_neg, neg_stream=None):

@@ -111,7 +111,11 @@ class ShardedTIP(TIP):
         self.coll.all_reduce_(deg)
         self.inv_deg_global = 1.0 / deg.clamp(min=1.0)
         self.plan_dst.inv_deg.copy_(self.inv_deg_global)
-        self.pos_plan = ops.cached_plan(self.local_idx, n, n_rel, by_src=False, doubled=True, rel_major=True, **kw)
+        # whole relations per rank: a mirrored edge set stays mirrored, and plan_dst then serves the decoder too
+        if self.n_local_rel and ops.edges_mirrored(self.local_idx, self.local_range):
+            self.pos_plan = self.plan_dst
+        else:
+            self.pos_plan = ops.cached_plan(self.local_idx, n, n_rel, by_src=False, doubled=True, rel_major=True, **kw)
         self._neg_local = None
         self._neg_plan_local = None
 
@@ -142,7 +146,7 @@ class ShardedTIP(TIP):
             self._neg_local = torch.empty_like(self.local_idx)
             self._neg_plan_local = ops.TypedCSR(self.local_idx.shape[1], d.n_drug, max(self.n_local_rel, 1), self.device,
                                                 by_src=False, doubled=True, rel_major=True)
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # sampler -> plan is the critical chain
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
