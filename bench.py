@@ -305,9 +305,7 @@ def run_b200_arm(args):
     #      from pinned host memory, rebuilds every index structure from them, trains one step and reads the loss back
     if static_loss is not None:
         loss_value = float(static_loss)
-    e2e = None
-    if world == 1:
-        e2e = measure_e2e(model, opt, data, args.steps, e_total)
+    e2e = measure_e2e(model, opt, data, args.steps, e_total, world)
     launches, launches_all = count_library_launches(step)   # every rank runs it: the step contains collectives
 
     if rank == 0:
@@ -319,9 +317,16 @@ def run_b200_arm(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / k_time / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_seg_aggregate<F=64> (R-GCN layer-1 edge pass)", "achieved": achieved,
+        traffic, traffic_src = None, None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the committed ncu --set full capture
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")))
+            traffic, traffic_src = t["traffic_bytes"], t["source"]
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": "k_seg_aggregate_flat<F=64> (R-GCN layer-1 edge pass)", "achieved": achieved,
                     "peak": peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_us": k_time * 1e6,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel_us": k_time * 1e6,
                     "algorithmic_bytes": alg_bytes, "compulsory_dram_bytes": compulsory,
                     "compulsory_frac": compulsory / k_time / 1e9 / peak, "segments": n_seg,
                     "note": "features are staged in shared memory: achieved counts gathered bytes (SURVEY 8d figure A), "
@@ -351,8 +356,10 @@ def run_b200_arm(args):
         os._exit(0)
 
 
-def measure_e2e(model, opt, data, steps, e_total):
-    from tip_b200 import ops
+def measure_e2e(model, opt, data, steps, e_total, world=1):
+    """every rank copies the graph tensors from its pinned host memory and rebuilds its index structures; wall clock
+    between barriers, max over ranks"""
+    import torch.distributed as dist
     dev = model.device
     names = ("dd_train_idx", "dd_train_et", "dd_train_range", "pp_train_indices", "dp_edge_index", "d_norm")
     host = {k: data[k].contiguous().pin_memory() for k in names}
@@ -366,20 +373,32 @@ def measure_e2e(model, opt, data, steps, e_total):
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)
         loss.backward()
+        if world > 1:
+            model.sync_gradients()
         opt.step()
         return loss.item()                    # device -> host
 
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(2):
         e2e_step()
-    torch.cuda.synchronize()
+    fence()
     t0 = time.perf_counter()
     for _ in range(steps):
         e2e_step()
-    torch.cuda.synchronize()
+    fence()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": 4.0 * e_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t)
+    return {"value": 4.0 * e_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
             "ms_per_step": dt * 1e3,
-            "what": "pinned-host graph tensors -> device, all typed CSRs / bitmaps rebuilt, one train step, loss.item()"}
+            "what": "per rank: pinned-host graph tensors -> device, all typed CSRs / bitmaps rebuilt, one train step, "
+                    "loss.item(); wall clock between barriers, max over ranks"}
 
 
 def main():

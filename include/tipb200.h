@@ -212,6 +212,17 @@ int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* stream_words
                     int64_t* neg_edge_index /* [2,n_edges] */, int32_t* status, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* ---------------------------------------------------------------- per-relation evaluation
+ * Replaces TIP.compute_auprc_auroc_ap_by_et / auprc_auroc_ap (src/layers.py:353-375, src/utils.py:86-93), i.e. 861
+ * x three scikit-learn calls on host copies: for relation r the 2k scores [pos_score[start:end], neg_score[start:end]]
+ * with targets [1]*k + [0]*k give record[0,r] = area under the precision-recall curve (trapezoid, sklearn.metrics.auc
+ * of precision_recall_curve), record[1,r] = roc_auc_score, record[2,r] = average_precision_score; ties are grouped
+ * per distinct score as scikit-learn does.  range_list must be the cumulative [start,end) table.  record is a
+ * DEVICE array of 3*n_rel doubles; a relation with an empty class gives NaN (scikit-learn raises there). */
+size_t tipb_eval_workspace_bytes(int64_t n_edges, int64_t n_rel);
+int tipb_eval_auprc_auroc_ap(const float* pos_score, const float* neg_score, const int64_t* range_list, int64_t n_edges,
+                             int64_t n_rel, double* record /* [3, n_rel] */, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -528,3 +528,134 @@ def test_bce_loss_mirrored_edge_set_uses_the_by_target_plan():
         close(loss, ref, rtol=1e-5, what="loss")
         close(dz, z64.grad, what="dz")
         close(dw, w64.grad, what="dw")
+
+
+# =============================================================================== BASELINE.json configs 3 and 4 (reduced)
+def _model_vs_oracle(model, data, mod, ns, state, grad_atol_rel=ATOL_REL):
+    from oracle import neg_sampling_oracle as nso
+    from oracle import tip_oracle as to
+    loss = model()
+    loss.backward()
+    mt = nso.MT19937()
+    mt.set_state(state)
+    neg = nso.typed_negative_sampling(mt, data["dd_train_idx"].numpy(), data["n_drug"], data["dd_train_range"].numpy())
+    assert np.array_equal(neg, model._neg_index.cpu().numpy()), "negative pairs differ from the oracle"
+    params = {n: p.detach().cpu().clone().requires_grad_(True) for n, p in model.named_parameters()}
+    orc = to.TipOracle(params, data["n_drug"], data["n_prot"], mod=mod, structural=True)
+    cpu = {k: v for k, v in data.items() if torch.is_tensor(v) and not v.is_sparse}
+    ref_loss, ref_z = orc.loss(cpu, torch.from_numpy(neg))
+    ref_loss.backward()
+    close(model.embeddings, ref_z, what="z")
+    close(loss, ref_loss, rtol=1e-5, what="loss")
+    for n, p in model.named_parameters():
+        close(p.grad, params[n].grad, atol_rel=grad_atol_rel, what="grad " + n)
+
+
+def test_scaled_shape_ten_thousand_drugs():
+    """BASELINE.json config 4 at reduced edge/relation count: 10^4 drugs -> 27-bit rejection mask, float32 row = perm/N
+    differs from floor division, feature matrices and z no longer fit in shared memory (L2 gather paths)."""
+    from tip_b200 import layers, neg_sampling as ns, synth
+    d = dev()
+    data = synth.make_tip_data(n_drug=10_000, n_prot=3_000, n_rel=6, dd_undirected=120_000, pp_undirected=9_000,
+                               pd_edges=4_000, seed=4)
+    torch.manual_seed(1111)
+    ns.seed(1111, d)
+    settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
+    model = layers.TIP(settings, d, mod="cat", data=data)
+    # 36 k signed terms per decoder-weight entry: entries that cancel to ~1e-3 of the largest one carry the fp32
+    # summation noise of BOTH implementations (the oracle runs in fp32 too), hence the wider absolute floor
+    _model_vs_oracle(model, data, "cat", ns, ns.get_state(d), grad_atol_rel=1e-4)
+
+
+def test_dd_only_rgcn_net():
+    """BASELINE.json config 3 (test/dd_net_scalable.py:51-77): embed[N,64] -> MyRGCNConv2(64,32) -> ReLU ->
+    MyRGCNConv2(32,16) -> ReLU with n_base = 16, DistMult decoder, typed negatives, BCE loss -- D-D graph only."""
+    from oracle import neg_sampling_oracle as nso
+    from oracle import tip_oracle as to
+    from tip_b200 import layers, neg_sampling as ns, ops, synth
+    d = dev()
+    data = synth.make_tip_data(n_drug=645, n_prot=50, n_rel=60, dd_undirected=150_000, pp_undirected=100, pd_edges=20,
+                               seed=3)
+    n, r = data["n_drug"], data["n_dd_et"]
+    idx, et, rl = data["dd_train_idx"].to(d), data["dd_train_et"].to(d), data["dd_train_range"].to(d).long()
+    torch.manual_seed(7)
+    embed = torch.nn.Parameter(torch.randn(n, 64, device=d))
+    conv1 = layers.MyRGCNConv2(64, 32, r, 16, after_relu=False).to(d)
+    conv2 = layers.MyRGCNConv2(32, 16, r, 16, after_relu=True).to(d)
+    dec = layers.MultiInnerProductDecoder(16, r).to(d)
+    ns.seed(99, d)
+    state = ns.get_state(d)
+    z = torch.relu(conv2(torch.relu(conv1(embed, idx, et, rl)), idx, et, rl))
+    neg = ns.typed_negative_sampling(idx, n, rl)
+    pos_s, neg_s = dec(z, idx, et), dec(z, neg, et)
+    loss = -torch.log(pos_s + 1e-13).mean() - torch.log(1 - neg_s + 1e-13).mean()
+    loss.backward()
+    # oracle, fp64
+    mt = nso.MT19937()
+    mt.set_state(state)
+    neg_ref = nso.typed_negative_sampling(mt, data["dd_train_idx"].numpy(), n, data["dd_train_range"].numpy())
+    assert np.array_equal(neg.cpu().numpy(), neg_ref)
+    P = lambda t: t.detach().cpu().double().requires_grad_(True)
+    e64, p1, p2, w64 = P(embed), [P(conv1.basis), P(conv1.att), P(conv1.root)], [P(conv2.basis), P(conv2.att), P(conv2.root)], P(dec.weight)
+    ci, ce, cr = data["dd_train_idx"], data["dd_train_et"], data["dd_train_range"].long()
+    h = torch.relu(to.rgcn_conv_vectorized(e64, ci, ce, p1[1], p1[0], p1[2]))
+    zr = torch.relu(to.rgcn_conv_vectorized(h, ci, ce, p2[1], p2[0], p2[2]))
+    ref = to.tip_loss(to.decoder(zr, ci, ce, w64), to.decoder(zr, torch.from_numpy(neg_ref), ce, w64))
+    ref.backward()
+    close(z, zr, what="z")
+    close(loss, ref, rtol=1e-5, what="loss")
+    for name, a, b in (("embed", embed, e64), ("basis1", conv1.basis, p1[0]), ("att1", conv1.att, p1[1]),
+                       ("root1", conv1.root, p1[2]), ("basis2", conv2.basis, p2[0]), ("att2", conv2.att, p2[1]),
+                       ("root2", conv2.root, p2[2]), ("dec.weight", dec.weight, w64)):
+        close(a.grad, b.grad, what="grad " + name)
+
+
+# =============================================================================== per-relation evaluation (SURVEY 8f rank 1)
+def test_eval_auprc_auroc_ap_matches_reference():
+    """tipb_eval_auprc_auroc_ap against the reference's own scikit-learn path (golden) and the oracle"""
+    import os
+    from oracle import eval_oracle as eo
+    from tip_b200 import ops
+    d = dev()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval.npz"))
+    rec = ops.eval_auprc_auroc_ap(T(g["pos"], d), T(g["neg"], d), T(g["range_list"], d))
+    assert rec.dtype == torch.float64 and tuple(rec.shape) == g["record"].shape
+    np.testing.assert_allclose(rec.cpu().numpy(), g["record"], rtol=0, atol=1e-12)
+    # polypharmacy-like test split: 300 relations, ~0.4 M pairs, quantised scores (many ties), one empty relation
+    rng = np.random.default_rng(8)
+    sizes = rng.integers(1, 3000, 300)
+    sizes[17] = 0
+    ends = np.cumsum(sizes)
+    rl = np.stack([ends - sizes, ends], axis=1).astype(np.int64)
+    e = int(ends[-1])
+    pos = (1 / (1 + np.exp(-rng.normal(1.0, 2.0, e)))).astype(np.float32)
+    neg = (1 / (1 + np.exp(-rng.normal(-1.0, 2.0, e)))).astype(np.float32)
+    pos[: e // 3] = np.round(pos[: e // 3], 2)
+    neg[: e // 3] = np.round(neg[: e // 3], 2)
+    rec = ops.eval_auprc_auroc_ap(T(pos, d), T(neg, d), T(rl, d)).cpu().numpy()
+    want = eo.record_by_relation(pos, neg, rl)
+    assert np.isnan(rec[:, 17]).all() and np.isnan(want[:, 17]).all()
+    ok = np.arange(300) != 17
+    np.testing.assert_allclose(rec[:, ok], want[:, ok], rtol=0, atol=1e-12)
+
+
+def test_tip_test_method_uses_the_gpu_evaluation(golden_layers):
+    """TIP.test() (src/layers.py:344-351): same record as the reference's host loop over scikit-learn"""
+    from tip_b200 import layers, neg_sampling as ns, synth
+    from tip_b200.utils import auprc_auroc_ap
+    d = dev()
+    data = synth.make_tip_data(n_drug=150, n_prot=500, n_rel=15, dd_undirected=9000, pp_undirected=2000, pd_edges=400,
+                               seed=12)
+    torch.manual_seed(1)
+    ns.seed(1, d)
+    settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
+    model = layers.TIP(settings, d, mod="cat", data=data)
+    record = model.test(print_output=False)
+    assert record.shape == (3, 15)
+    dd = model.data
+    with torch.no_grad():
+        pos = model.decoder(model.embeddings, dd.dd_test_idx, dd.dd_test_et).cpu()
+        neg = model.decoder(model.embeddings, model.test_neg_index, dd.dd_test_et).cpu()
+    for r, (a, b) in enumerate(dd.dd_test_range.cpu().tolist()):
+        want = auprc_auroc_ap(torch.cat([torch.ones(b - a), torch.zeros(b - a)]), torch.cat([pos[a:b], neg[a:b]]))
+        np.testing.assert_allclose(record[:, r], want, rtol=0, atol=1e-12)

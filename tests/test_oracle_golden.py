@@ -1,5 +1,7 @@
 """The oracle (oracle/*.py) against the golden vectors dumped from the reference's
 own code (oracle/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import torch
 
@@ -160,3 +162,20 @@ def test_full_model_matches_reference(golden_layers):
         mt.set_state(("MT19937", g[pre + "mt_key"], int(g[pre + "mt_pos"])))
         neg = nso.typed_negative_sampling(mt, g["data/dd_train_idx"], n_drug, g["data/dd_train_range"])
         assert np.array_equal(neg, g[pre + "neg"])
+
+
+def test_eval_oracle_matches_reference_auprc_auroc_ap():
+    """oracle/eval_oracle.py against tests/golden/eval.npz = outputs of the reference's own src/utils.py:86-93
+    (scikit-learn) on seeded scores with heavy ties, saturated scores and a one-pair relation"""
+    from oracle import eval_oracle as eo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval.npz"))
+    rec = eo.record_by_relation(g["pos"], g["neg"], g["range_list"])
+    np.testing.assert_allclose(rec, g["record"], rtol=0, atol=1e-14)
+    # and against scikit-learn directly (it is what the reference calls), fresh random scores
+    from tip_b200.utils import auprc_auroc_ap
+    import torch
+    rng = np.random.default_rng(5)
+    s = rng.random(400).astype(np.float32).round(2)
+    t = (rng.random(400) < 0.4).astype(np.float32)
+    want = auprc_auroc_ap(torch.from_numpy(t), torch.from_numpy(s))
+    np.testing.assert_allclose(eo.auprc_auroc_ap(t, s), want, rtol=0, atol=1e-14)

@@ -92,7 +92,13 @@ def _gpu_worker(rank, world, port, out):
     model = parallel.ShardedTIP(settings, dev, mod="cat", data=data, rank=rank, world=world)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     losses = []
-    for _ in range(2):
+    for it in range(2):
+        if it == 1:
+            # the graph tensors are overwritten in place (what bench.py's end-to-end loop does every step): the shard's
+            # index structures must be rebuilt and give the same numbers
+            for k in ("dd_train_idx", "dd_train_range", "pp_train_indices", "dp_edge_index"):
+                getattr(model.data, k).copy_(getattr(model.data, k).clone())
+            model.invalidate_graph_caches()
         opt.zero_grad()
         loss = model()
         loss.backward()

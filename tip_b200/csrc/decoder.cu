@@ -60,8 +60,9 @@ k_decoder_fwd(const float4* __restrict__ z, const float4* __restrict__ w, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// segment kernel.  smem: z [n_nodes * LPR] float4
-template <int LPR, int MODE>
+// segment kernel.  smem: z [n_nodes * LPR] float4 when it fits (STAGED), else rows come from L2 through the
+// read-only path (scaled graphs: 10^4 drugs x 16 floats = 640 KB)
+template <int LPR, int MODE, bool STAGED>
 __global__ void __launch_bounds__(512)
 k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ seg_rel,
               const int* __restrict__ other, const int* __restrict__ eid, const int* __restrict__ counts,
@@ -71,8 +72,11 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
     extern __shared__ float4 s_z[];
     constexpr int G = 32 / LPR;
     const int lane = lane_id(), g = lane / LPR, l = lane % LPR;
-    for (int i = threadIdx.x; i < n_nodes * LPR; i += blockDim.x) s_z[i] = z[i];
-    __syncthreads();
+    if (STAGED) {
+        for (int i = threadIdx.x; i < n_nodes * LPR; i += blockDim.x) s_z[i] = z[i];
+        __syncthreads();
+    }
+    const float4* __restrict__ zsrc = STAGED ? s_z : z;
 
     const int S = counts[TIPB_CSR_COUNT_SEGMENTS];
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -82,7 +86,7 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
     for (int s = warp_global; s < S; s += n_warps) {
         const int beg = seg_ptr[s], end = seg_ptr[s + 1];
         const int node = seg_node[s], rel = seg_rel[s];
-        const float4 zn = s_z[node * LPR + l];
+        const float4 zn = zsrc[node * LPR + l];
         const float4 wr = w[rel * LPR + l];
         const float4 u = f4_mul(zn, wr);
         float4 acc = f4_zero();
@@ -103,7 +107,7 @@ k_decoder_seg(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
             for (int r = 0; r < LPR; ++r) {
                 const int k = r * G + g;
                 const int j = __shfl_sync(FULL, idx, k);
-                zj[r] = s_z[j * LPR + l];
+                zj[r] = zsrc[j * LPR + l];
                 float p = f4_dot(u, zj[r]);
 #pragma unroll
                 for (int o = LPR >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
@@ -281,23 +285,26 @@ static int decoder_seg_run(const CsrView& v, int mode, const float* z, const flo
     const int n_warps = grid * 16;
     float* loss_part = c.take<float>(n_warps);
     float* dw_tmp = c.take<float>(size_t(v.n_rel) * dim);
-    const size_t smem = size_t(v.n_nodes) * dim * sizeof(float);
+    const bool staged = size_t(v.n_nodes) * dim * sizeof(float) + 1024 <= size_t(max_smem_optin());
+    const size_t smem = staged ? size_t(v.n_nodes) * dim * sizeof(float) : 0;
     // mult = 1: doubled plan (every pair listed under both endpoints); mult = 2: one listing per directed edge of a
     // mirrored edge set (each (node, relation) segment of the doubled plan would hold every neighbour twice)
     const float inv_count = n_edges > 0 ? float(mult) / float(n_edges) : 0.f;
     int rc;
-#define RUN(MODEV)                                                                                                  \
+#define RUN1(MODEV, STG)                                                                                            \
     {                                                                                                               \
-        auto kern = k_decoder_seg<LPR, MODEV>;                                                                      \
+        auto kern = k_decoder_seg<LPR, MODEV, STG>;                                                                 \
         if ((rc = ensure_dyn_smem((const void*)kern, smem))) return rc;                                             \
         kern<<<grid, 512, smem, s>>>(v.seg_ptr, v.seg_node, v.seg_rel, v.other, v.eid, v.counts, (const float4*)z,  \
                                      (const float4*)w, grad_out, (int)v.n_nodes, (int)n_edges, apply_sigmoid,       \
                                      inv_count, (float4*)acc_seg, (float4*)zacc_seg, loss_part);                    \
     }
+#define RUN(MODEV) { if (staged) RUN1(MODEV, true) else RUN1(MODEV, false) }
     if (mode == DEC_MODE_POS) RUN(DEC_MODE_POS)
     else if (mode == DEC_MODE_NEG) RUN(DEC_MODE_NEG)
     else RUN(DEC_MODE_GRAD)
 #undef RUN
+#undef RUN1
     k_decoder_node_reduce<<<(unsigned)v.n_nodes, NODE_REDUCE_THREADS, 0, s>>>(v.node_ptr, v.rel_seg, v.counts, acc_seg, dim, accumulate, d_z);
     if (accumulate) {
         k_rel_reduce<<<(unsigned)v.n_rel, REL_REDUCE_THREADS, 0, s>>>(v.rel_seg_ptr, v.rel_seg, v.counts, zacc_seg, dim, 0.5f, dw_tmp);
@@ -317,8 +324,6 @@ static int decoder_seg_dispatch(const void* plan, int mode, int64_t n_edges, int
                                 size_t ws_bytes, cudaStream_t s) {
     CsrView v = csr_view(plan, mult == 2 ? n_edges : 2 * n_edges, n_nodes, n_rel);
     TIPB_CHECK_ARG(ws_bytes >= dec_ws_bytes(v.seg_cap, n_rel, dim), "decoder: workspace too small");
-    TIPB_CHECK_ARG(size_t(n_nodes) * dim * 4 + 1024 <= size_t(max_smem_optin()),
-                   "decoder: z (%lld x %d) does not fit in shared memory", (long long)n_nodes, dim);
     switch (dim) {
         case 4: return decoder_seg_run<1>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);
         case 8: return decoder_seg_run<2>(v, mode, z, w, grad_out, n_edges, apply_sigmoid, accumulate, mult, loss_out, d_z, d_w, ws, s);

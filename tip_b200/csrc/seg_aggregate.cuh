@@ -212,6 +212,9 @@ k_seg_aggregate_flat(const int* __restrict__ seg_ptr, const int* __restrict__ ot
     const int eb = seg_ptr[s], ee = seg_ptr[s_end];
     const int zero_row = n_rows;
     const uint32_t lane_addr = uint32_t(__cvta_generic_to_shared(s_feat)) + uint32_t((F >= 32 ? lane : (lane & (F - 1))) * FPL * 4);
+    // the block's 32 row offsets are broadcast through a per-warp shared-memory slot (one STS, then uniform LDS.128:
+    // four offsets per load) -- a SHFL per entry costs two LSU wavefronts and made the kernel LSU-pipe bound
+    const uint32_t slot = uint32_t(__cvta_generic_to_shared(s_feat + (n_rows + 1) * LPR)) + uint32_t(threadIdx.x >> 5) * 128u;
 
     int b = eb & ~31;
     int idx, e_t;
@@ -235,10 +238,16 @@ k_seg_aggregate_flat(const int* __restrict__ seg_ptr, const int* __restrict__ ot
             idx_n = pn < ee ? ld_stream_i32(other + pn) : zero_row;
             e_n = seg_ptr[min(s + __popc(flags) + 1 + lane, S)];
         }
+        __syncwarp();
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot + uint32_t(lane) * 4u), "r"(uint32_t(idx) * uint32_t(F * 4)) : "memory");
+        __syncwarp();
+        uint32_t offs[4];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const int j = __shfl_sync(FULL, idx, k);
-            const uint32_t a = lane_addr + uint32_t(j) * uint32_t(F * 4);
+            if ((k & 3) == 0)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(offs[0]), "=r"(offs[1]), "=r"(offs[2]), "=r"(offs[3]) : "r"(slot + uint32_t(k) * 4u));
+            const uint32_t a = lane_addr + offs[k & 3];
             if (FPL == 1) {
                 float v;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -273,7 +282,7 @@ k_seg_aggregate_flat(const int* __restrict__ seg_ptr, const int* __restrict__ ot
 template <int F>
 static int seg_aggregate_launch_flat(const CsrView& v, const float* feat, const float* row_scale,
                                      const float* relu_ref, int n_rows, float* out, cudaStream_t s) {
-    const size_t bytes = size_t(n_rows + 1) * F * sizeof(float);
+    const size_t bytes = size_t(n_rows + 1) * F * sizeof(float) + 32 * 128;  // rows + zero row + per-warp offset slots
     auto kern = k_seg_aggregate_flat<F>;
     if (int rc = ensure_dyn_smem((const void*)kern, bytes)) return rc;
     kern<<<sm_count(), 1024, bytes, s>>>(v.seg_ptr, v.other, v.counts, (const float4*)feat, row_scale,
@@ -310,7 +319,7 @@ static inline bool seg_aggregate_supported(int f) { return f == 4 || f == 8 || f
 
 static int seg_aggregate_launch(const CsrView& v, const float* feat, const float* row_scale, const float* relu_ref,
                                 int n_rows, int f, float* out, cudaStream_t s) {
-    if (f >= 16 && size_t(n_rows + 1) * f * sizeof(float) + 1024 <= size_t(max_smem_optin())) {
+    if (f >= 16 && size_t(n_rows + 1) * f * sizeof(float) + 32 * 128 + 1024 <= size_t(max_smem_optin())) {
         switch (f) {
             case 16: return seg_aggregate_launch_flat<16>(v, feat, row_scale, relu_ref, n_rows, out, s);
             case 32: return seg_aggregate_launch_flat<32>(v, feat, row_scale, relu_ref, n_rows, out, s);

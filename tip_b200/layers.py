@@ -393,15 +393,9 @@ class TIP(nn.Module):
         return self.compute_auprc_auroc_ap_by_et(pos_score, neg_score, d.dd_test_range, print_output)
 
     def compute_auprc_auroc_ap_by_et(self, pos_score, neg_score, dd_range, print_out):
-        from .utils import auprc_auroc_ap
-        record = np.zeros((3, self.data.n_dd_et))
-        pos_score, neg_score, dd_range = pos_score.cpu(), neg_score.cpu(), dd_range.cpu()
-        for i in range(dd_range.shape[0]):
-            start, end = int(dd_range[i][0]), int(dd_range[i][1])
-            p_s, n_s = pos_score[start:end], neg_score[start:end]
-            score = torch.cat([p_s, n_s])
-            target = torch.cat([torch.ones(p_s.shape[0]), torch.zeros(n_s.shape[0])])
-            record[0, i], record[1, i], record[2, i] = auprc_auroc_ap(target, score)
+        """src/layers.py:353-375; the 861 x 3 scikit-learn calls on host copies become one segmented sort + scan on the
+        device (ops.eval_auprc_auroc_ap), one device->host copy of the 3 x n_rel record at the end"""
+        record = ops.eval_auprc_auroc_ap(pos_score, neg_score, dd_range).cpu().numpy()
         if print_out:
             auprc, auroc, ap = record.sum(axis=1) / self.data.n_dd_et
             print("On test set: auprc:{:0.4f}   auroc:{:0.4f}   ap@50:{:0.4f}    ".format(auprc, auroc, ap))

@@ -402,5 +402,22 @@ def decoder_sweep(z, weight, sigmoid=True):
     return out
 
 
-__all__ = ["TypedCSR", "cached_plan", "rgcn_conv", "gcn_norm", "gcn_spmm", "hier_conv", "decoder_score", "bce_loss",
+def eval_auprc_auroc_ap(pos_score, neg_score, range_list):
+    """record[3, n_rel] (float64, on the device): auprc, auroc, ap per relation -- src/layers.py:353-369 without the
+    861 host round trips"""
+    pos_score, neg_score = _f32c(pos_score.detach()), _f32c(neg_score.detach())
+    if not pos_score.is_cuda:
+        raise _lib.TipbError("eval_auprc_auroc_ap takes CUDA tensors only (there is no CPU path)")
+    rl = _i64c(range_list.to(device=pos_score.device, dtype=torch.long))
+    n_edges, n_rel = pos_score.numel(), rl.shape[0]
+    assert neg_score.numel() == n_edges and rl.dim() == 2 and rl.shape[1] == 2
+    L = lib()
+    record = torch.empty((3, n_rel), dtype=torch.float64, device=pos_score.device)
+    ws = workspace(L.tipb_eval_workspace_bytes(n_edges, n_rel), pos_score.device, "eval")
+    check(L.tipb_eval_auprc_auroc_ap(ptr(pos_score), ptr(neg_score), ptr(rl), n_edges, n_rel, ptr(record), ptr(ws),
+                                     ws.numel(), stream()), "eval_auprc_auroc_ap")
+    return record
+
+
+__all__ = ["eval_auprc_auroc_ap", "TypedCSR", "cached_plan", "rgcn_conv", "gcn_norm", "gcn_spmm", "hier_conv", "decoder_score", "bce_loss",
            "decoder_sweep", "workspace", "math"]

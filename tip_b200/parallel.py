@@ -119,6 +119,22 @@ class ShardedTIP(TIP):
         self._neg_local = None
         self._neg_plan_local = None
 
+    def invalidate_graph_caches(self):
+        """the graph tensors were overwritten in place: re-derive this rank's shard and rebuild its index structures
+        (same buffers), including the global degrees"""
+        super().invalidate_graph_caches()
+        d = self.data
+        self.local_idx.copy_(d.dd_train_idx[:, self.e_lo:self.e_hi])
+        self.local_range.copy_(d.dd_train_range[self.r_lo:self.r_hi] - self.e_lo)
+        rl = self.local_range if self.n_local_rel else None
+        plans = [self.plan_dst, self.plan_src] + ([self.pos_plan] if self.pos_plan is not self.plan_dst else [])
+        for plan in plans:
+            plan.build(self.local_idx, None, rl)
+            plan._versions = ops._versions(self.local_idx, None, rl)
+        deg = self.plan_dst.field("deg").to(torch.float32).clone()
+        self.coll.all_reduce_(deg)
+        self.plan_dst.inv_deg.copy_(1.0 / deg.clamp(min=1.0))
+
     # ---- one R-GCN layer on this rank's relations
     def _rgcn_local(self, conv, x, relu):
         x = _ReduceBwd.apply(x, self.coll)
