@@ -166,6 +166,27 @@ k_seg_aggregate(const int* __restrict__ seg_ptr, const int* __restrict__ other, 
 // when entry k is the last of its segment the accumulator is stored as that segment's row.  Segment ends inside a
 // block come from 32 prefetched seg_ptr values and one warp OR-reduction; the next block's indices are prefetched.
 // Lanes outside the warp's range carry the index of an all-zero row.
+// acc[0..FPL) += the FPL floats at shared-memory byte address a
+template <int FPL>
+__device__ __forceinline__ void flat_add(float (&acc)[FPL], uint32_t a) {
+    if (FPL == 1) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        acc[0] += v;
+    } else if (FPL == 2) {
+        float v0, v1;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v0), "=f"(v1) : "r"(a));
+        const float2 t = __fadd2_rn(make_float2(acc[0], acc[1]), make_float2(v0, v1));
+        acc[0] = t.x; acc[1] = t.y;
+    } else {
+        float v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(a));
+        const float2 t0 = __fadd2_rn(make_float2(acc[0], acc[1]), make_float2(v0, v1));
+        const float2 t1 = __fadd2_rn(make_float2(acc[2], acc[3]), make_float2(v2, v3));
+        acc[0] = t0.x; acc[1] = t0.y; acc[2] = t1.x; acc[3] = t1.y;
+    }
+}
+
 template <int F>
 __global__ void __launch_bounds__(1024)
 k_seg_aggregate_flat(const int* __restrict__ seg_ptr, const int* __restrict__ other, const int* __restrict__ counts,
@@ -241,37 +262,31 @@ k_seg_aggregate_flat(const int* __restrict__ seg_ptr, const int* __restrict__ ot
         __syncwarp();
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot + uint32_t(lane) * 4u), "r"(uint32_t(idx) * uint32_t(F * 4)) : "memory");
         __syncwarp();
-        uint32_t offs[4];
+        // four entries per trip; a trip without a segment end (3 of 4 on the drug graph) takes the branch-free path:
+        // predicating the store/reset on every entry costs more issue slots than the gather itself
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if ((k & 3) == 0)
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(offs[0]), "=r"(offs[1]), "=r"(offs[2]), "=r"(offs[3]) : "r"(slot + uint32_t(k) * 4u));
-            const uint32_t a = lane_addr + offs[k & 3];
-            if (FPL == 1) {
-                float v;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-                acc[0] += v;
-            } else if (FPL == 2) {
-                float v0, v1;
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v0), "=f"(v1) : "r"(a));
-                const float2 t = __fadd2_rn(make_float2(acc[0], acc[1]), make_float2(v0, v1));
-                acc[0] = t.x; acc[1] = t.y;
+        for (int k4 = 0; k4 < 32; k4 += 4) {
+            uint32_t offs[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(offs[0]), "=r"(offs[1]), "=r"(offs[2]), "=r"(offs[3]) : "r"(slot + uint32_t(k4) * 4u));
+            const unsigned m4 = (flags >> k4) & 15u;
+            if (m4 == 0u) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) flat_add<FPL>(acc, lane_addr + offs[q]);
             } else {
-                float v0, v1, v2, v3;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(a));
-                const float2 t0 = __fadd2_rn(make_float2(acc[0], acc[1]), make_float2(v0, v1));
-                const float2 t1 = __fadd2_rn(make_float2(acc[2], acc[3]), make_float2(v2, v3));
-                acc[0] = t0.x; acc[1] = t0.y; acc[2] = t1.x; acc[3] = t1.y;
-            }
-            if (flags & (1u << k)) {
-                float* dst = out + int64_t(s) * F + (F >= 32 ? lane : (lane & (F - 1))) * FPL;
-                if (FPL == 1) { if (F >= 32 || lane < F) dst[0] = acc[0]; }
-                else if (FPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
-                else *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 #pragma unroll
-                for (int q2 = 0; q2 < FPL; ++q2) acc[q2] = 0.f;
-                ++s;
+                for (int q = 0; q < 4; ++q) {
+                    flat_add<FPL>(acc, lane_addr + offs[q]);
+                    if (m4 & (1u << q)) {
+                        float* dst = out + int64_t(s) * F + (F >= 32 ? lane : (lane & (F - 1))) * FPL;
+                        if (FPL == 1) { if (F >= 32 || lane < F) dst[0] = acc[0]; }
+                        else if (FPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
+                        else *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+                        for (int q2 = 0; q2 < FPL; ++q2) acc[q2] = 0.f;
+                        ++s;
+                    }
+                }
             }
         }
         idx = idx_n;
