@@ -233,8 +233,11 @@ def run_b200_arm(args):
         model = parallel.ShardedTIP(settings_for(args.mod), dev, mod=args.mod, data=data, rank=rank, world=world)
     else:
         model = layers.TIP(settings_for(args.mod), dev, mod=args.mod, data=data)
-    opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True,
-                           fused=os.environ.get("TIPB_BENCH_FUSED_ADAM", "1") == "1")
+    if os.environ.get("TIPB_BENCH_TORCH_ADAM") == "1":
+        opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True, fused=True)
+    else:       # tip.py:21 `torch.optim.Adam(model.parameters(), lr)` as one launch of the library (csrc/adam.cu)
+        from tip_b200 import optim
+        opt = optim.Adam(model.parameters(), lr=model.settings.lr)
 
     def step():
         opt.zero_grad(set_to_none=True)

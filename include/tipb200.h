@@ -223,6 +223,16 @@ size_t tipb_eval_workspace_bytes(int64_t n_edges, int64_t n_rel);
 int tipb_eval_auprc_auroc_ap(const float* pos_score, const float* neg_score, const int64_t* range_list, int64_t n_edges,
                              int64_t n_rel, double* record /* [3, n_rel] */, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- optimiser step
+ * torch.optim.Adam(model.parameters(), lr).step() of tip.py:21-30 (defaults: betas 0.9/0.999, eps 1e-8, no weight
+ * decay, no amsgrad) for all parameter tensors in one launch.  params/grads/exp_avg/exp_avg_sq are HOST arrays of
+ * n_tensors device pointers (fp32, numel[k] elements each); step_dev is one device float holding the number of steps
+ * taken so far, advanced by the call (CUDA-graph capturable: no host state). */
+int tipb_adam_max_tensors(void);
+int tipb_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                   void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                   float* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -659,3 +659,37 @@ def test_tip_test_method_uses_the_gpu_evaluation(golden_layers):
     for r, (a, b) in enumerate(dd.dd_test_range.cpu().tolist()):
         want = auprc_auroc_ap(torch.cat([torch.ones(b - a), torch.zeros(b - a)]), torch.cat([pos[a:b], neg[a:b]]))
         np.testing.assert_allclose(record[:, r], want, rtol=0, atol=1e-12)
+
+
+# =============================================================================== optimiser step
+def test_fused_adam_matches_torch_adam():
+    """tip_b200.optim.Adam (one launch over all tensors) against torch.optim.Adam, the optimiser of tip.py:21"""
+    from tip_b200 import optim
+    d = dev()
+    torch.manual_seed(0)
+    shapes = [(32, 19081), (32,), (16, 32), (645, 48), (861, 32), (32, 64, 32), (1,), (4097,), (0,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=d)) for s in shapes]
+    my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=0.01)
+    mine = optim.Adam(my_p, lr=0.01)
+    for it in range(5):
+        for a, b in zip(ref_p, my_p):
+            g = torch.randn_like(a) * (10.0 ** (it - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        mine.step()
+    for a, b, s in zip(ref_p, my_p, shapes):
+        close(b, a, rtol=2e-6, atol_rel=1e-7, what="param %s" % (s,))
+        if a.numel():
+            close(mine.state[b]["exp_avg"], ref.state[a]["exp_avg"], rtol=2e-6, atol_rel=1e-7, what="exp_avg")
+            close(mine.state[b]["exp_avg_sq"], ref.state[a]["exp_avg_sq"], rtol=2e-6, atol_rel=1e-7, what="exp_avg_sq")
+    assert float(mine.param_groups[0]["step"]) == 5.0
+    # parameters without a gradient are skipped, CPU parameters are refused
+    extra = torch.nn.Parameter(torch.ones(3, device=d))
+    o2 = optim.Adam([extra], lr=0.1)
+    o2.step()
+    assert torch.equal(extra.detach(), torch.ones(3, device=d))
+    cpu_p = torch.nn.Parameter(torch.ones(3))
+    cpu_p.grad = torch.ones(3)
+    with pytest.raises(Exception):
+        optim.Adam([cpu_p], lr=0.1).step()

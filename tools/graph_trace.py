@@ -6,14 +6,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from tip_b200 import layers, neg_sampling as ns
+from tip_b200 import layers, neg_sampling as ns, optim
 from torch.profiler import ProfilerActivity, profile
 
 dev = torch.device("cuda:0")
 data, _ = bench.make_data("polypharmacy")
 torch.manual_seed(1111); ns.seed(1111, dev)
 model = layers.TIP(bench.settings_for("cat"), dev, mod="cat", data=data)
-opt = torch.optim.Adam(model.parameters(), lr=0.01, capturable=True, fused=True)
+opt = optim.Adam(model.parameters(), lr=0.01)
 
 def step():
     opt.zero_grad(set_to_none=True)

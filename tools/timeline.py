@@ -5,13 +5,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from tip_b200 import layers, neg_sampling as ns, ops
+from tip_b200 import layers, neg_sampling as ns, optim, ops
 
 dev = torch.device("cuda:0")
 data, _ = bench.make_data("polypharmacy")
 torch.manual_seed(1111); ns.seed(1111, dev)
 model = layers.TIP(bench.settings_for("cat"), dev, mod="cat", data=data)
-opt = torch.optim.Adam(model.parameters(), lr=0.01, capturable=True, fused=True)
+opt = optim.Adam(model.parameters(), lr=0.01)
 
 def ev(stream=None):
     e = torch.cuda.Event(enable_timing=True)
