@@ -230,7 +230,7 @@ int tipb_eval_auprc_auroc_ap(const float* pos_score, const float* neg_score, con
  * taken so far, advanced by the call (CUDA-graph capturable: no host state). */
 int tipb_adam_max_tensors(void);
 int tipb_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                   void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                   void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
                    float* step_dev, void* stream);
 
 #ifdef __cplusplus

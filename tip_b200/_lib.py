@@ -51,7 +51,7 @@ SIGNATURES = {
     "tipb_eval_workspace_bytes": (_sz, [_i64, _i64]),
     "tipb_eval_auprc_auroc_ap": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "tipb_adam_max_tensors": (C.c_int, []),
-    "tipb_adam_step": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, _p, _p]),
+    "tipb_adam_step": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, _p, _p]),
     "tipb_mt19937_seed": (C.c_int, [_p, _u32, _p]),
     "tipb_mt19937_stream_words": (_i64, [_i64]),
     "tipb_mt19937_generate": (C.c_int, [_p, _p, _i64, _p]),

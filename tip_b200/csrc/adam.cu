@@ -23,11 +23,12 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256)
-k_adam(const AdamTable tab, float lr, float beta1, float beta2, float eps, const float* __restrict__ step_in) {
+k_adam(const AdamTable tab, float lr, float beta1, float beta2, float omb1, float omb2, float eps,
+       const float* __restrict__ step_in) {
     // step_in holds t-1; every CTA derives the same bias corrections (the counter itself is advanced by k_adam_tick)
     // (bias corrections in double, as torch derives them from Python floats)
     const double t = double(step_in[0]) + 1.0;
-    const double bc1 = 1.0 - pow(double(beta1), t), bc2 = 1.0 - pow(double(beta2), t);
+    const double bc1 = 1.0 - pow(1.0 - double(omb1), t), bc2 = 1.0 - pow(1.0 - double(omb2), t);
     const float step_size = float(double(lr) / bc1), rb2 = float(sqrt(bc2));
     int lo = 0, hi = tab.count - 1;
     const int c = blockIdx.x;
@@ -44,8 +45,8 @@ k_adam(const AdamTable tab, float lr, float beta1, float beta2, float eps, const
     for (int64_t i = base + threadIdx.x; i < base + ADAM_CHUNK && i < n; i += 256) {
         const float gi = g[i];
         float mi = m[i], vi = v[i];
-        mi = mi + (gi - mi) * (1.0f - beta1);
-        vi = vi * beta2 + (1.0f - beta2) * gi * gi;
+        mi = mi + (gi - mi) * omb1;              // lerp(m, g, 1 - beta1)
+        vi = vi * beta2 + omb2 * (gi * gi);      // mul_(beta2).addcmul_(g, g, value = 1 - beta2)
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) / rb2 + eps;
@@ -64,8 +65,9 @@ extern "C" {
 int tipb_adam_max_tensors(void) { return ADAM_MAX_TENSORS; }
 
 int tipb_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                   void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                   void* const* exp_avg_sq, const int64_t* numel, double lr_d, double beta1_d, double beta2_d, double eps_d,
                    float* step_dev, void* stream) {
+    const float lr = float(lr_d), beta1 = float(beta1_d), beta2 = float(beta2_d), eps = float(eps_d);
     TIPB_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numel)) && step_dev,
                    "adam_step: NULL argument");
     TIPB_CHECK_ARG(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
@@ -93,7 +95,10 @@ int tipb_adam_step(int n_tensors, void* const* params, const void* const* grads,
         }
         tab.chunk_begin[used] = chunks;
         tab.count = used;
-        if (chunks > 0) k_adam<<<chunks, 256, 0, s>>>(tab, lr, beta1, beta2, eps, step_dev);
+        // 1 - beta is formed in double (as torch forms it from Python floats): 1.0f - 0.999f is off by 1.3e-5
+        if (chunks > 0)
+            k_adam<<<chunks, 256, 0, s>>>(tab, lr, beta1, beta2, float(1.0 - double(beta1_d)), float(1.0 - double(beta2_d)), eps,
+                                          step_dev);
     }
     k_adam_tick<<<1, 1, 0, s>>>(step_dev);
     TIPB_CHECK_LAUNCH("adam_step");

@@ -12,6 +12,11 @@
 namespace tipb {
 
 constexpr int TILED_THREADS = 256;
+// One CTA per node: 645 CTAs on the drug graph.  At 4 resident CTAs per SM (592 slots) that is 1.09 waves -- the last
+// 53 CTAs run alone; capping registers for 5 per SM (740 slots) keeps the whole grid resident in one wave.
+#ifndef TILED_MIN_CTAS
+#define TILED_MIN_CTAS 5
+#endif
 constexpr int CHT = 32;  // segments per staged chunk
 // float4 slots of the staging area: two stages of payload + att rows, and never less than the
 // TILED_THREADS * 4 slots the split-K partial tiles need when they reuse it
@@ -45,7 +50,7 @@ __device__ __forceinline__ void stage_tiled(float4* sP, float4* sA, const float4
 // smem (float4 units): stage [2][CHT*TF] | att [2][CHT*NBQ] | Gs [B*TF] | then floats: xs [F_IN] | red [256]
 // (the split-K partials alias the staging area once the main loop is done)
 template <int TF, int NBQ>
-__global__ void __launch_bounds__(TILED_THREADS)
+__global__ void __launch_bounds__(TILED_THREADS, TILED_MIN_CTAS)
 k_rgcn_node_fwd_tiled(const int* __restrict__ node_ptr, const int* __restrict__ seg_rel, const float* __restrict__ inv_deg,
                       const float4* __restrict__ H, const float4* __restrict__ att4, const float* __restrict__ basis,
                       const float* __restrict__ root, const float* __restrict__ bias, const float* __restrict__ x,
@@ -170,7 +175,7 @@ __device__ __forceinline__ bool d_att_writer(int tx, int& b_local) {
 
 // smem (float4 units): stage [2][CHT*TFO] | att [2][CHT*NBQ] | Ys [B*TFO] | Qs [B*TFO] | floats: Ds [CHT*B] | xs [f_in] | gs [F_OUT]
 template <int TFO, int NBQ>
-__global__ void __launch_bounds__(TILED_THREADS)
+__global__ void __launch_bounds__(TILED_THREADS, TILED_MIN_CTAS)
 k_rgcn_node_bwd_tiled(const int* __restrict__ node_ptr, const int* __restrict__ seg_rel, const float4* __restrict__ T,
                       const float4* __restrict__ att4, const float4* __restrict__ basis4,
                       const float4* __restrict__ root4, const float* __restrict__ x, const float* __restrict__ geff,

@@ -300,8 +300,10 @@ static int seg_aggregate_launch_flat(const CsrView& v, const float* feat, const 
     const size_t bytes = size_t(n_rows + 1) * F * sizeof(float) + 32 * 128;  // rows + zero row + per-warp offset slots
     auto kern = k_seg_aggregate_flat<F>;
     if (int rc = ensure_dyn_smem((const void*)kern, bytes)) return rc;
-    kern<<<sm_count(), 1024, bytes, s>>>(v.seg_ptr, v.other, v.counts, (const float4*)feat, row_scale,
-                                         (const float4*)relu_ref, n_rows, out);
+    // two resident CTAs per SM when two copies of the feature matrix fit (F <= 32 on the drug graph)
+    const int per_sm = 2 * (bytes + 1024) <= size_t(max_smem_optin()) ? 2 : 1;
+    kern<<<sm_count() * per_sm, 1024, bytes, s>>>(v.seg_ptr, v.other, v.counts, (const float4*)feat, row_scale,
+                                                  (const float4*)relu_ref, n_rows, out);
     TIPB_CHECK_LAUNCH("seg_aggregate_flat");
     return TIPB_OK;
 }
