@@ -45,13 +45,13 @@ def parse():
     return ap.parse_args()
 
 
-def make_data(shape):
+def make_data(shape, mod="cat"):
     from tip_b200 import synth
     if shape == "small":
         return synth.make_tip_data(n_drug=200, n_prot=2000, n_rel=40, dd_undirected=60_000, pp_undirected=20_000,
                                    pd_edges=2_000, seed=1111), "synthetic small (debug) shape"
     return synth.make_tip_data(**synth.POLYPHARMACY, seed=1112), \
-        "TIP-cat train step, synthetic polypharmacy shape: 645 drugs, 19081 proteins, 861 relations"
+        "TIP-%s train step, synthetic polypharmacy shape: 645 drugs, 19081 proteins, 861 relations" % mod
 
 
 def settings_for(mod):
@@ -152,7 +152,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    data, workload = make_data(args.shape)
+    data, workload = make_data(args.shape, args.mod)
     res = time_cpu_reference(data, args.mod, args.cpu_sample_relations, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
@@ -224,7 +224,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     from tip_b200 import layers, neg_sampling as ns
 
-    data, workload = make_data(args.shape)
+    data, workload = make_data(args.shape, args.mod)
     e_total = int(data["dd_train_idx"].shape[1])
     torch.manual_seed(1111)
     ns.seed(1111, dev)

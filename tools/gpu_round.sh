@@ -8,8 +8,13 @@ mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; grep -n "^E  \|passed\|failed\|^FAILED" $O/${TAG}_pytest.log | head
 timeout 600 python bench.py --steps 30 --warmup 5 > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err; echo "bench rc=$?"
 cat $O/${TAG}_bench_n1.json
+timeout 300 python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/${TAG}_smoke.log
+timeout 300 python bench.py --mod add --steps 30 --warmup 5 --skip-cpu-baseline > $O/${TAG}_bench_add_n1.json 2> $O/${TAG}_bench_add_n1.err; echo "TIP-add: $(grep -o '"ms_per_step": [0-9.]*' $O/${TAG}_bench_add_n1.json | head -1)"
+timeout 120 python tools/ubench_sweep.py > $O/${TAG}_sweep.json 2> $O/${TAG}_sweep.err; cat $O/${TAG}_sweep.json
+if [ "$WITH_REFERENCE_ARM" = "1" ]; then
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; echo "reference arm rc=$?"
 cat $O/${TAG}_bench_reference.json
+fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_eager.csv \
     python tools/one_step.py 3 > $O/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
 read SKIP_ALL SKIP_TOP <<< $(python - <<PY
@@ -33,4 +38,5 @@ ncu -i /tmp/${TAG}_top.ncu-rep --page raw --csv > $O/${TAG}_top_raw.csv 2>/dev/n
 for k in k_seg_aggregate_flat k_decoder_seg k_grp_place; do
     ncu -i /tmp/${TAG}_top.ncu-rep --page source --csv --kernel-name regex:$k --launch-count 1 > $O/${TAG}_src_$k.csv 2>/dev/null
 done
+timeout 200 python tools/graph_trace.py $O/${TAG}_graph_trace.txt > $O/${TAG}_graph_trace.log 2>&1; echo "graph trace rc=$?"; head -1 $O/${TAG}_graph_trace.txt
 du -sm $O
