@@ -693,3 +693,18 @@ def test_fused_adam_matches_torch_adam():
     cpu_p.grad = torch.ones(3)
     with pytest.raises(Exception):
         optim.Adam([cpu_p], lr=0.1).step()
+
+
+@pytest.mark.parametrize("n,r,dim", [(645, 5, 16), (97, 3, 8), (130, 2, 32), (64, 2, 4), (129, 3, 12), (3000, 1, 16)])
+def test_decoder_sweep_all_widths(n, r, dim):
+    """BASELINE.json config 5 kernel: the register-tiled sweep (dim in {4, 8, 16, 32}, z in shared memory), and the
+    generic kernel for other widths / larger graphs, against a float64 einsum"""
+    from tip_b200 import ops
+    d = dev()
+    torch.manual_seed(n + dim)
+    z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
+    ref = torch.einsum("ik,rk,jk->rij", z.double(), w.double(), z.double())
+    out = ops.decoder_sweep(z.to(d), w.to(d), sigmoid=False)
+    assert tuple(out.shape) == (r, n, n)
+    close(out, ref, what="sweep values")
+    close(ops.decoder_sweep(z.to(d), w.to(d), sigmoid=True), torch.sigmoid(ref), what="sweep scores")
