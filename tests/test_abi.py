@@ -137,6 +137,34 @@ def test_no_cpu_fallback():
         dec(torch.randn(5, 4), ei, torch.zeros(4, dtype=torch.long))
     with pytest.raises(TipbError):
         layers.typed_negative_sampling(ei, 5, torch.tensor([[0, 4]]))
+    # the later additions refuse host tensors too: evaluation, mirrored-layout check, sweep, optimiser
+    from tip_b200 import ops, optim
+    with pytest.raises(TipbError):
+        ops.eval_auprc_auroc_ap(torch.rand(4), torch.rand(4), torch.tensor([[0, 4]]))
+    with pytest.raises(TipbError):
+        ops.edges_mirrored(ei, torch.tensor([[0, 4]]))
+    with pytest.raises(TipbError):
+        ops.decoder_sweep(torch.randn(5, 4), torch.randn(3, 4))
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(TipbError):
+        optim.Adam([p], lr=0.1).step()
+    with pytest.raises(ValueError):
+        optim.Adam([p], lr=-1.0)
+
+
+def test_adam_argument_checks_need_no_gpu():
+    """tipb_adam_step validates its host-side arguments before any launch"""
+    import ctypes as C
+    from tip_b200 import _lib
+    L = _lib.lib()
+    assert L.tipb_adam_max_tensors() >= 13          # the 13 parameter tensors of TIP in one launch
+    rc = L.tipb_adam_step(1, None, None, None, None, None, 0.01, 0.9, 0.999, 1e-8, None, None)
+    assert rc == -1 and b"adam_step" in L.tipb_last_error()
+    one = (C.c_void_p * 1)(8)
+    n = (C.c_int64 * 1)(4)
+    rc = L.tipb_adam_step(1, one, one, one, one, n, 0.01, 1.5, 0.999, 1e-8, one, None)
+    assert rc == -1 and b"hyper-parameter" in L.tipb_last_error()
 
 
 def test_product_never_imports_the_oracle():
