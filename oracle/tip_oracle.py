@@ -154,9 +154,12 @@ class TipOracle(object):
     SURVEY.md section 8c item 4).  `structural=True` keeps the reference's op order
     (861-iteration loops); False uses the reassociated R-GCN."""
 
-    param_names = ("encoder.pp_encoder.conv1.bias", "encoder.pp_encoder.conv1.lin.weight",
+    # TIP.named_parameters() order of the reference as executed (golden tip_*/param/*): a module's own parameters
+    # (`embed`) come before those of its sub-modules, whatever the assignment order in __init__ (src/layers.py:503-516)
+    param_names = ("encoder.embed",
+                   "encoder.pp_encoder.conv1.bias", "encoder.pp_encoder.conv1.lin.weight",
                    "encoder.pp_encoder.conv2.bias", "encoder.pp_encoder.conv2.lin.weight",
-                   "encoder.embed", "encoder.hgcn.weight",
+                   "encoder.hgcn.weight",
                    "encoder.rgcn1.basis", "encoder.rgcn1.att", "encoder.rgcn1.root",
                    "encoder.rgcn2.basis", "encoder.rgcn2.att", "encoder.rgcn2.root",
                    "decoder.weight")

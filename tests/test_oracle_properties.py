@@ -1,0 +1,193 @@
+"""Property tests of the oracle itself (CPU only; SURVEY.md section 4 test plan): the three R-GCN forms agree on
+hypothesis-generated graphs with the edge cases the domain has (empty relation, isolated node -> count clamp to 1,
+duplicate edges, self pairs), autograd of the oracle passes `gradcheck` in float64, the numpy MT19937 / typed
+negative sampler equal numpy and the reference's own function on generated inputs, and the evaluation oracle equals
+scikit-learn on generated score vectors with ties.  A wrong oracle would make every GPU parity claim void."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import eval_oracle as eo
+from oracle import layout_oracle as lo
+from oracle import neg_sampling_oracle as nso
+from oracle import tip_oracle as to
+
+REF = "/root/reference"
+SET = settings(max_examples=25, deadline=None, derandomize=True)
+
+
+@st.composite
+def typed_graphs(draw, max_nodes=9, max_rel=4, max_edges=30):
+    n = draw(st.integers(2, max_nodes))
+    r = draw(st.integers(1, max_rel))
+    sizes = [draw(st.integers(0, max_edges // r)) for _ in range(r)]      # empty relations allowed
+    e = sum(sizes)
+    src = draw(st.lists(st.integers(0, n - 1), min_size=e, max_size=e))
+    dst = draw(st.lists(st.integers(0, max(n - 2, 0)), min_size=e, max_size=e))   # node n-1 never a target: isolated
+    ei = torch.tensor([src, dst], dtype=torch.long).reshape(2, e)
+    et = torch.repeat_interleave(torch.arange(r), torch.tensor(sizes))
+    ends = np.cumsum(sizes)
+    rl = torch.tensor(np.stack([ends - sizes, ends], axis=1), dtype=torch.long).reshape(r, 2)
+    return n, r, ei, et, rl
+
+
+@SET
+@given(typed_graphs(), st.integers(0, 2 ** 16))
+def test_rgcn_forms_agree_on_generated_graphs(g, seed):
+    n, r, ei, et, rl = g
+    gen = torch.Generator().manual_seed(seed)
+    fi, fo, nb = 3, 2, 2
+    x = torch.randn(n, fi, generator=gen, dtype=torch.float64)
+    att = torch.randn(r, nb, generator=gen, dtype=torch.float64)
+    basis = torch.randn(nb, fi, fo, generator=gen, dtype=torch.float64)
+    root = torch.randn(fi, fo, generator=gen, dtype=torch.float64)
+    a = to.rgcn_conv_structural(x, ei, rl, att, basis, root)
+    b = to.rgcn_conv_bmm(x, ei, et, att, basis, root)
+    c = to.rgcn_conv_vectorized(x, ei, et, att, basis, root)
+    torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(a, c, rtol=1e-12, atol=1e-12)
+    # a node without incoming edges only keeps its root term (mean over zero edges = 0, count clamped to 1)
+    torch.testing.assert_close(a[n - 1], x[n - 1] @ root, rtol=1e-12, atol=1e-12)
+    # MyRGCNConv accepts edge types in any order: permuting the edges does not change the result
+    if ei.shape[1] > 1:
+        perm = torch.randperm(ei.shape[1], generator=gen)
+        torch.testing.assert_close(to.rgcn_conv_bmm(x, ei[:, perm], et[perm], att, basis, root), a, rtol=1e-10, atol=1e-10)
+
+
+def _tiny_graph():
+    ei = torch.tensor([[0, 1, 2, 2, 3, 0, 1, 4], [1, 0, 1, 3, 2, 2, 1, 0]])
+    et = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2])
+    rl = torch.tensor([[0, 3], [3, 5], [5, 8]])
+    return 5, ei, et, rl
+
+
+def test_oracle_autograd_passes_gradcheck():
+    n, ei, et, rl = _tiny_graph()
+    gen = torch.Generator().manual_seed(3)
+    mk = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float64, requires_grad=True)
+    x, att, basis, root = mk(n, 3), mk(3, 2), mk(2, 3, 2), mk(3, 2)
+    assert torch.autograd.gradcheck(lambda *a: to.rgcn_conv_structural(a[0], ei, rl, *a[1:]), (x, att, basis, root))
+    assert torch.autograd.gradcheck(lambda *a: to.rgcn_conv_vectorized(a[0], ei, et, *a[1:]), (x, att, basis, root))
+    # hierarchy conv: 3 sources, 2 targets
+    xh, wh = mk(5, 2), mk(2, 3)
+    eh = torch.tensor([[0, 1, 2, 2], [3, 3, 4, 3]])
+    assert torch.autograd.gradcheck(lambda a, b: to.hier_conv(a, eh, b, 3, 2), (xh, wh))
+    # GCN layer over the normalised graph (self loops added once, duplicates kept)
+    pp = torch.tensor([[0, 1, 1, 2, 3, 3], [1, 0, 2, 1, 3, 0]])
+    norm = to.gcn_norm(pp, 4, torch.float64)
+    xg, wg, bg = mk(4, 3), mk(2, 3), mk(2)
+    assert torch.autograd.gradcheck(lambda a, b, c: to.gcn_conv(a, norm, b, c), (xg, wg, bg))
+    # decoder + loss
+    z, w = mk(n, 4), mk(3, 4)
+    neg = torch.tensor([[4, 3, 0, 1, 2, 3, 4, 0], [4, 0, 2, 2, 1, 0, 3, 1]])
+    assert torch.autograd.gradcheck(lambda a, b: to.tip_loss(to.decoder(a, ei, et, b), to.decoder(a, neg, et, b)), (z, w))
+
+
+def test_decoder_is_symmetric_and_loss_matches_the_reference_formula():
+    n, ei, et, _ = _tiny_graph()
+    gen = torch.Generator().manual_seed(9)
+    z, w = torch.randn(n, 4, generator=gen), torch.randn(3, 4, generator=gen)
+    s = to.decoder(z, ei, et, w)
+    torch.testing.assert_close(s, to.decoder(z, ei.flip(0), et, w))          # DistMult: z_i^T diag(w_r) z_j
+    neg = to.decoder(z, ei.flip(1), et, w)
+    want = -torch.log(s + 1e-13).mean() - torch.log(1 - neg + 1e-13).mean()   # src/layers.py:338-340
+    torch.testing.assert_close(to.tip_loss(s, neg), want)
+
+
+@SET
+@given(st.integers(0, 2 ** 32 - 1), st.integers(1, 700))
+def test_mt19937_oracle_equals_numpy_for_any_seed(seed, count):
+    mt = nso.MT19937(seed)
+    rs = np.random.RandomState(seed)
+    assert np.array_equal(mt.choice(645 * 645, count), rs.choice(645 * 645, count))
+    st_np = rs.get_state()
+    assert np.array_equal(mt.key, st_np[1]) and mt.pos == st_np[2]
+
+
+def _reference_neg_sampling():
+    if not os.path.isdir(os.path.join(REF, "src")):
+        pytest.skip("the reference tree is only present in the build container")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src.neg_sampling import typed_negative_sampling      # the reference's own function, unmodified
+    return typed_negative_sampling
+
+
+@settings(max_examples=15, deadline=None, derandomize=True)
+@given(st.integers(3, 40), st.lists(st.integers(0, 60), min_size=1, max_size=5), st.integers(0, 2 ** 31 - 1))
+def test_neg_sampling_oracle_equals_the_live_reference(n, sizes, seed):
+    """dense relations force the retry loop (and its indexing quirk, src/neg_sampling.py:12-16) to run"""
+    ref_fn = _reference_neg_sampling()
+    rng = np.random.default_rng(seed)
+    sizes = [min(s, n * n - 1) for s in sizes]
+    e = sum(sizes)
+    pos = rng.integers(0, n, (2, e)).astype(np.int64)
+    ends = np.cumsum(sizes)
+    rl = np.stack([ends - sizes, ends], axis=1).astype(np.int64)
+    np.random.seed(seed % (2 ** 32))
+    want = ref_fn(torch.from_numpy(pos), n, torch.from_numpy(rl)).numpy()
+    mt = nso.MT19937(seed % (2 ** 32))
+    got = nso.typed_negative_sampling(mt, pos, n, rl)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    st_np = np.random.get_state()
+    assert np.array_equal(mt.key, st_np[1]) and mt.pos == st_np[2]
+
+
+@SET
+@given(typed_graphs(max_nodes=12, max_rel=5, max_edges=60), st.booleans(), st.booleans())
+def test_typed_csr_definition_properties(g, by_src, rel_major):
+    """the index structure the CUDA builder must reproduce bit for bit: a stable grouping of the edge ids"""
+    n, r, ei, et, rl = g
+    csr = lo.typed_csr(ei.numpy(), et.numpy(), n, r, by="src" if by_src else "dst", rel_major=rel_major)
+    e = ei.shape[1]
+    eid, other, seg_ptr = csr["eid"], csr["other"], csr["seg_ptr"]
+    assert sorted(eid.tolist()) == list(range(e))                        # a permutation of the edges
+    node_col, other_col = (0, 1) if by_src else (1, 0)
+    assert np.array_equal(other, ei.numpy()[other_col][eid])
+    assert seg_ptr[0] == 0 and seg_ptr[-1] == e and np.all(np.diff(seg_ptr) > 0)      # no empty segment
+    keys = []
+    for s in range(len(seg_ptr) - 1):
+        ids = eid[seg_ptr[s]:seg_ptr[s + 1]]
+        assert np.all(np.diff(ids) > 0)                                  # input order inside a segment (stable)
+        assert np.all(ei.numpy()[node_col][ids] == csr["seg_node"][s]) and np.all(et.numpy()[ids] == csr["seg_rel"][s])
+        keys.append((csr["seg_rel"][s], csr["seg_node"][s]) if rel_major else (csr["seg_node"][s], csr["seg_rel"][s]))
+    assert keys == sorted(set(keys))                                      # segments strictly ordered, no duplicates
+
+
+@SET
+@given(st.lists(st.tuples(st.integers(0, 20), st.booleans()), min_size=2, max_size=120))
+def test_eval_oracle_equals_scikit_learn_with_ties(items):
+    from sklearn import metrics
+    score = np.array([s for s, _ in items], dtype=np.float32) / 20.0      # few distinct values: many ties
+    y = np.array([t for _, t in items], dtype=np.float64)
+    if y.min() == y.max():
+        assert all(np.isnan(v) for v in eo.auprc_auroc_ap(y, score))
+        return
+    auprc, auroc, ap = eo.auprc_auroc_ap(y, score)
+    p, r, _ = metrics.precision_recall_curve(y, score)
+    np.testing.assert_allclose(auprc, metrics.auc(r, p), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(auroc, metrics.roc_auc_score(y, score), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ap, metrics.average_precision_score(y, score), rtol=0, atol=1e-12)
+    # AUROC of the complemented labels mirrors around 1/2; a monotone map of the scores changes nothing
+    np.testing.assert_allclose(eo.auprc_auroc_ap(1 - y, score)[1], 1 - auroc, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(eo.auprc_auroc_ap(y, np.exp(score))[1], auroc, rtol=0, atol=1e-12)
+
+
+def test_parameter_names_and_order_match_the_reference_state_dict():
+    """parameter order drives state_dict / Adam order; checkpoints of the reference must carry over.  The golden file
+    holds TIP.named_parameters() of the reference's own class as executed (oracle/make_golden.py)."""
+    from tip_b200 import layers
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "layers.npz"))
+    golden = tuple(k[len("tip_cat/param/"):] for k in g.files if k.startswith("tip_cat/param/"))
+    torch.manual_seed(0)
+    enc = layers.FMEncoder("cpu", 30, 4, 50, 50, 30, 16, 32, 48, 32, 16, mod="cat")
+    names = ["encoder." + n for n, _ in enc.named_parameters()] + ["decoder.weight"]
+    assert tuple(names) == golden == to.TipOracle.param_names
+    shapes = {n: tuple(p.shape) for n, p in enc.named_parameters()}
+    assert shapes["rgcn1.basis"] == (32, 64, 32) and shapes["rgcn1.att"] == (4, 32) and shapes["rgcn1.root"] == (64, 32)
+    assert shapes["rgcn2.basis"] == (32, 32, 16) and shapes["embed"] == (30, 48) and shapes["hgcn.weight"] == (16, 16)
+    assert shapes["pp_encoder.conv1.lin.weight"] == (32, 50) and shapes["pp_encoder.conv2.lin.weight"] == (16, 32)
