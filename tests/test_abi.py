@@ -153,6 +153,15 @@ def test_no_cpu_fallback():
         optim.Adam([p], lr=-1.0)
 
 
+def test_range_table_validation():
+    from tip_b200 import ops
+    ops.check_cumulative_ranges(torch.tensor([[0, 3], [3, 3], [3, 9]]), 9)
+    for bad, e in ((torch.tensor([[0, 3], [4, 9]]), 9), (torch.tensor([[0, 3], [3, 8]]), 9), (torch.tensor([[1, 9]]), 9),
+                   (torch.tensor([[0, 5], [5, 4]]), 4)):
+        with pytest.raises(ValueError):
+            ops.check_cumulative_ranges(bad, e)
+
+
 def test_adam_argument_checks_need_no_gpu():
     """tipb_adam_step validates its host-side arguments before any launch"""
     import ctypes as C

@@ -7,6 +7,7 @@ back to torch ops when the library is missing (tip_b200._lib raises).
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -402,6 +403,15 @@ def decoder_sweep(z, weight, sigmoid=True):
     return out
 
 
+def check_cumulative_ranges(range_list, n_edges):
+    """range_list must be the cumulative [start, end) table of src/utils.py:26-32 tiling [0, n_edges)"""
+    rl = np.asarray(range_list.detach().cpu() if torch.is_tensor(range_list) else range_list).astype(np.int64)
+    ok = rl.ndim == 2 and rl.shape[1] == 2 and rl.shape[0] > 0
+    ok = ok and rl[0, 0] == 0 and rl[-1, 1] == n_edges and np.all(rl[:, 1] >= rl[:, 0]) and np.all(rl[1:, 0] == rl[:-1, 1])
+    if not ok:
+        raise ValueError("range_list must be the cumulative [start,end) table of src/utils.py:26-32 covering every edge")
+
+
 def eval_auprc_auroc_ap(pos_score, neg_score, range_list):
     """record[3, n_rel] (float64, on the device): auprc, auroc, ap per relation -- src/layers.py:353-369 without the
     861 host round trips"""
@@ -411,6 +421,7 @@ def eval_auprc_auroc_ap(pos_score, neg_score, range_list):
     rl = _i64c(range_list.to(device=pos_score.device, dtype=torch.long))
     n_edges, n_rel = pos_score.numel(), rl.shape[0]
     assert neg_score.numel() == n_edges and rl.dim() == 2 and rl.shape[1] == 2
+    check_cumulative_ranges(rl, n_edges)          # evaluation is not on the training path: one small host copy
     L = lib()
     record = torch.empty((3, n_rel), dtype=torch.float64, device=pos_score.device)
     ws = workspace(L.tipb_eval_workspace_bytes(n_edges, n_rel), pos_score.device, "eval")
