@@ -122,13 +122,21 @@ def cpu_reference_step_factory(data, mod, n_sample_rel):
     mt = nso.MT19937(1111)
     pos_np, rl_np = d["dd_train_idx"].numpy(), rl.numpy()
 
-    def step():
+    def step(phases=None):
+        t = [time.perf_counter()]
         opt.zero_grad()
         neg = torch.from_numpy(nso.typed_negative_sampling(mt, pos_np, data["n_drug"], rl_np))
+        t.append(time.perf_counter())
         loss, _ = orc.loss(d, neg)
+        t.append(time.perf_counter())
         loss.backward()
+        t.append(time.perf_counter())
         opt.step()
-        return float(loss)
+        t.append(time.perf_counter())
+        if phases is not None:
+            for name, a, b in zip(("neg_sampling", "forward", "backward", "adam"), t[:-1], t[1:]):
+                phases[name] = b - a
+        return float(loss.detach())
 
     return step, e_s, n_rel
 

@@ -181,8 +181,11 @@ int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int
  *                 built ON THE HOST from host copies of range_list and the popcounts (tipb_neg_table_build,
  *                 no CUDA call); totals[0..3] = sum_L, sum_W, highest accepted index a window may touch,
  *                 expected accepted values consumed.
- *   status        0 ok; bit0: stream_words too short; bit1: retry-round table overflow (exact mode);
- *                 bit2: an offset left its bracket -- restore mt_state and call again with exact_mode = 1. */
+ *   status        STICKY device word, never cleared by the library: every failed call ORs its bits in (bit0:
+ *                 stream_words too short; bit1: retry-round table overflow (exact mode); bit2: an offset left its
+ *                 bracket -- call again with exact_mode = 1).  A failed call leaves mt_state untouched (it consumed
+ *                 nothing), so calls that are not checked on the host (CUDA-graph replay) cannot silently drift: the
+ *                 caller reads the word whenever it likes and clears it itself. */
 int tipb_mt19937_seed(uint32_t* mt_state, uint32_t seed, void* stream);
 int64_t tipb_mt19937_stream_words(int64_t n_new); /* rounds n_new up to the generator's granularity (454) */
 int tipb_mt19937_generate(const uint32_t* mt_state, uint32_t* stream_words /* [624 + n_new] */, int64_t n_new,

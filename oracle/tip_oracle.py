@@ -84,6 +84,31 @@ def rgcn_conv_vectorized(x, edge_index, edge_type, att, basis, root, bias=None):
     return out if bias is None else out + bias
 
 
+def typed_adjacency(edge_index, edge_type, n_nodes, n_rel, dtype):
+    """(R*N) x N count matrix A[(r, i), j] = number of edges j -> i of relation r (sparse COO, coalesced) and the
+    in-degree of every node over ALL relations: the data `rgcn_conv_sparse` needs, built once per graph."""
+    seg = edge_type * n_nodes + edge_index[1]
+    a = torch.sparse_coo_tensor(torch.stack([seg, edge_index[0]]), torch.ones(edge_index.shape[1], dtype=dtype),
+                                (n_rel * n_nodes, n_nodes)).coalesce()
+    count = torch.zeros(n_nodes, dtype=dtype).index_add_(0, edge_index[1],
+                                                         torch.ones(edge_index.shape[1], dtype=dtype))
+    return a, count
+
+
+def rgcn_conv_sparse(x, adjacency, att, basis, root, bias=None):
+    """`rgcn_conv_vectorized` without its E x F_in gather: H = A X as one sparse-dense product (O(E) memory for A,
+    O(R N F_in) for H).  This is the form the full benchmark workload (861 relations, 8.28 M edges) is checked
+    against in fp64; tests/test_oracle_properties.py cross-checks it against the structural form at <= 50 relations."""
+    a, count = adjacency
+    n, fi = x.shape
+    n_rel = att.shape[0]
+    h = torch.sparse.mm(a, x)                                           # [R*N, F_in]
+    w = rgcn_relation_weights(att, basis)                               # [R, F_in, F_out]
+    agg = h.view(n_rel, n, fi).permute(1, 0, 2).reshape(n, n_rel * fi) @ w.reshape(n_rel * fi, -1)
+    out = agg / count.clamp(min=1).unsqueeze(1) + x @ root
+    return out if bias is None else out + bias
+
+
 # --------------------------------------------------------------------------- P-P GCN
 def gcn_norm(edge_index, n_nodes, dtype):
     """PyG 2.0.1 gcn_norm with add_remaining_self_loops (called once, then cached,
@@ -164,17 +189,22 @@ class TipOracle(object):
                    "encoder.rgcn2.basis", "encoder.rgcn2.att", "encoder.rgcn2.root",
                    "decoder.weight")
 
-    def __init__(self, params, n_drug, n_prot, mod="cat", structural=True):
+    def __init__(self, params, n_drug, n_prot, mod="cat", structural=True, sparse=False):
         assert mod in ("cat", "add")
         self.p = params
-        self.n_drug, self.n_prot, self.mod, self.structural = n_drug, n_prot, mod, structural
+        self.n_drug, self.n_prot, self.mod, self.structural, self.sparse = n_drug, n_prot, mod, structural, sparse
         self._pp_cache = None
+        self._dd_cache = None
 
     def _rgcn(self, name, x, ei, et, rl):
         p = self.p
         args = (p[f"encoder.{name}.att"], p[f"encoder.{name}.basis"], p[f"encoder.{name}.root"])
         if self.structural:
             return rgcn_conv_structural(x, ei, rl, *args)
+        if self.sparse:     # full-scale form: the typed adjacency is built once (like the CSR plans of the product)
+            if self._dd_cache is None:
+                self._dd_cache = typed_adjacency(ei, et, x.shape[0], args[0].shape[0], x.dtype)
+            return rgcn_conv_sparse(x, self._dd_cache, *args)
         return rgcn_conv_vectorized(x, ei, et, *args)
 
     def encode(self, d):

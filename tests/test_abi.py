@@ -194,3 +194,27 @@ def test_init_draw_order_matches_reference_modules(golden_layers):
     assert torch.equal(x, torch.from_numpy(golden_layers["rgcn2/x"]))
     for name in ("att", "root", "basis"):
         assert torch.equal(getattr(conv, name).data, torch.from_numpy(golden_layers[f"rgcn2/{name}"])), name
+
+
+def test_adam_state_layout_is_torchs():
+    """the step counter must live in state[p] (as torch.optim.Adam keeps it), never in param_groups, and a
+    loaded state_dict must make the optimiser re-derive its device counter (checked on the GPU in
+    test_fused_adam_matches_torch_adam; here: the host-side bookkeeping, no launch)."""
+    import torch
+    from tip_b200 import optim
+    from tip_b200._lib import TipbError
+    p = [torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(2, 2))]
+    ref = torch.optim.Adam(p, lr=0.1)
+    for q in p:
+        q.grad = torch.ones_like(q)
+    ref.step()
+    ref.step()
+    mine = optim.Adam(p, lr=0.1)
+    mine._counters[0] = "stale"
+    mine.load_state_dict(ref.state_dict())
+    assert mine._counters == {}                                       # re-derived at the next step
+    assert "step" not in mine.state_dict()["param_groups"][0]
+    assert "step" not in optim.Adam(p, lr=0.1).state_dict()["param_groups"][0]
+    assert all(float(mine.state[q]["step"]) == 2.0 for q in p)
+    with pytest.raises(TipbError):                                    # CPU parameters: no CPU path
+        mine.step()

@@ -683,7 +683,30 @@ def test_fused_adam_matches_torch_adam():
         if a.numel():
             close(mine.state[b]["exp_avg"], ref.state[a]["exp_avg"], rtol=2e-6, atol_rel=1e-7, what="exp_avg")
             close(mine.state[b]["exp_avg_sq"], ref.state[a]["exp_avg_sq"], rtol=2e-6, atol_rel=1e-7, what="exp_avg_sq")
-    assert float(mine.param_groups[0]["step"]) == 5.0
+    assert all(float(mine.state[b]["step"]) == 5.0 for b in my_p if b.numel())
+    assert "step" not in mine.param_groups[0]          # torch's layout: the counter lives in state[p] only
+    # state_dict round trips, both ways and through the CPU (torch.load(..., map_location="cpu")):
+    # torch.optim.Adam -> tip_b200.optim.Adam must continue the SAME trajectory (bias correction uses `step`)
+    import copy
+    sd = copy.deepcopy(ref.state_dict())
+    for st in sd["state"].values():
+        for k, v in st.items():
+            st[k] = v.cpu() if torch.is_tensor(v) else v
+    resumed_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    resumed = optim.Adam(resumed_p, lr=0.01)
+    resumed.load_state_dict(sd)
+    back_p = [torch.nn.Parameter(p.detach().clone()) for p in my_p]
+    back = torch.optim.Adam(back_p, lr=0.01)
+    back.load_state_dict(copy.deepcopy(mine.state_dict()))
+    for a, b, c_, e_ in zip(ref_p, my_p, resumed_p, back_p):
+        g = torch.randn_like(a)
+        a.grad, b.grad, c_.grad, e_.grad = g.clone(), g.clone(), g.clone(), g.clone()
+    ref.step(); mine.step(); resumed.step(); back.step()
+    for a, b, c_, e_, s in zip(ref_p, my_p, resumed_p, back_p, shapes):
+        close(c_, a, rtol=2e-6, atol_rel=1e-7, what="resumed from a torch state_dict %s" % (s,))
+        close(e_, a, rtol=2e-6, atol_rel=1e-7, what="torch resumed from our state_dict %s" % (s,))
+        close(b, a, rtol=2e-6, atol_rel=1e-7, what="param after 6 steps %s" % (s,))
+    assert all(float(resumed.state[c_]["step"]) == 6.0 for c_ in resumed_p if c_.numel())
     # parameters without a gradient are skipped, CPU parameters are refused
     extra = torch.nn.Parameter(torch.ones(3, device=d))
     o2 = optim.Adam([extra], lr=0.1)
@@ -708,3 +731,82 @@ def test_decoder_sweep_all_widths(n, r, dim):
     assert tuple(out.shape) == (r, n, n)
     close(out, ref, what="sweep values")
     close(ops.decoder_sweep(z.to(d), w.to(d), sigmoid=True), torch.sigmoid(ref), what="sweep scores")
+
+
+# =============================================================================== the benched workload itself
+# bench.py times TIP-cat / TIP-add on synth.make_tip_data(**POLYPHARMACY, seed=1112): 645 drugs, 19,081 proteins,
+# 861 relations, 8.28 M directed typed edges (hub rows with ~10^5 addends, 29 chain blocks, 64 MT19937 chunks).
+# These tests pin THAT instance: negatives bit-exact over two consecutive steps incl. the final MT19937 state, and
+# z / loss / all 13 gradients against the fp64 oracle (sparse reassociated form, cross-checked against the structural
+# form on the CPU in tests/test_oracle_properties.py).  Tolerance: fp32 rtol 1e-4 (north_star).
+_BENCH_DATA = {}
+
+
+def _bench_data():
+    if "d" not in _BENCH_DATA:
+        import bench
+        _BENCH_DATA["d"] = bench.make_data("polypharmacy")[0]       # exactly what bench.py builds
+    return _BENCH_DATA["d"]
+
+
+def _fullscale_oracle(named_params, data, mod, neg, chunk=1 << 20):
+    """fp64 loss / z / gradients of the whole model at full scale: encoder through TipOracle(sparse=True); the two
+    decoder passes are evaluated in edge chunks with their gradient accumulated chunk by chunk (O(chunk) memory)."""
+    from oracle import tip_oracle as to
+    params = {n: p.detach().cpu().double().clone().requires_grad_(True) for n, p in named_params}
+    orc = to.TipOracle(params, data["n_drug"], data["n_prot"], mod=mod, structural=False, sparse=True)
+    cpu = {k: v for k, v in data.items() if torch.is_tensor(v) and not v.is_sparse}
+    z = orc.encode(cpu)
+    zl = z.detach().clone().requires_grad_(True)
+    w = params["decoder.weight"]
+    idx, et = cpu["dd_train_idx"], cpu["dd_train_et"]
+    neg = torch.from_numpy(neg)
+    e = idx.shape[1]
+    total = 0.0
+    for a in range(0, e, chunk):
+        b = min(e, a + chunk)
+        part = -(torch.log(to.decoder(zl, idx[:, a:b], et[a:b], w) + to.EPS).sum() +
+                 torch.log(1 - to.decoder(zl, neg[:, a:b], et[a:b], w) + to.EPS).sum()) / e
+        part.backward()
+        total += float(part)
+    z.backward(zl.grad)
+    return total, z.detach(), {n: p.grad for n, p in params.items()}
+
+
+@pytest.mark.parametrize("mod", ["cat", "add"])
+def test_benched_workload_parity(mod):
+    import bench
+    from oracle import neg_sampling_oracle as nso
+    from tip_b200 import layers, neg_sampling as ns
+    d = dev()
+    data = _bench_data()
+    torch.manual_seed(1111)
+    ns.seed(1111, d)
+    model = layers.TIP(bench.settings_for(mod), d, mod=mod, data=data)
+    state0 = ns.get_state(d)
+    loss = model()                      # check_status=True: a bracket miss / short stream would be rerun exactly
+    loss.backward()
+    neg1 = model._neg_index.cpu().numpy().copy()
+    z1 = model.embeddings.detach().clone()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    model(check_status=False)           # second consecutive step, the unchecked (CUDA-graph) flavour
+    neg2 = model._neg_index.cpu().numpy().copy()
+    assert ns.last_status(d) == 0
+    state2 = ns.get_state(d)
+    # ---- (a) negatives of both steps and the final stream state, bit for bit
+    mt = nso.MT19937()
+    mt.set_state(state0)
+    pos_np, rl_np = data["dd_train_idx"].numpy(), data["dd_train_range"].numpy()
+    ref1 = nso.typed_negative_sampling(mt, pos_np, data["n_drug"], rl_np)
+    assert np.array_equal(neg1, ref1), "step-1 negatives differ from the oracle"
+    ref2 = nso.typed_negative_sampling(mt, pos_np, data["n_drug"], rl_np)
+    assert np.array_equal(neg2, ref2), "step-2 negatives differ from the oracle"
+    want = mt.get_state()
+    assert np.array_equal(state2[1], want[1]) and state2[2] == want[2], "MT19937 state after two steps"
+    # ---- (b) z, loss and all 13 gradients against the fp64 oracle
+    ref_loss, ref_z, ref_grads = _fullscale_oracle(model.named_parameters(), data, mod, ref1)
+    close(z1, ref_z, what="z")
+    close(loss, np.float64(ref_loss), rtol=1e-5, what="loss")
+    assert len(grads) == 13
+    for n_, g in grads.items():
+        close(g, ref_grads[n_], what="grad " + n_)

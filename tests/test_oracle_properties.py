@@ -191,3 +191,44 @@ def test_parameter_names_and_order_match_the_reference_state_dict():
     assert shapes["rgcn1.basis"] == (32, 64, 32) and shapes["rgcn1.att"] == (4, 32) and shapes["rgcn1.root"] == (64, 32)
     assert shapes["rgcn2.basis"] == (32, 32, 16) and shapes["embed"] == (30, 48) and shapes["hgcn.weight"] == (16, 16)
     assert shapes["pp_encoder.conv1.lin.weight"] == (32, 50) and shapes["pp_encoder.conv2.lin.weight"] == (16, 32)
+
+
+def test_fullscale_oracle_form_equals_the_structural_form():
+    """The benched workload (861 relations, 8.28 M edges) is checked on the GPU against TipOracle(sparse=True) in fp64
+    (tests/test_gpu_parity.py::test_benched_workload_parity), because the reference's own op order costs O(R*E*F) in
+    backward.  Here that form is cross-checked against the STRUCTURAL form (the reference's op order, per-relation loops)
+    on a 48-relation instance with the model's real widths (64 -> 32 -> 16, 32 bases): loss, z and all 13 gradients."""
+    from oracle import neg_sampling_oracle as nso
+    from oracle import tip_oracle as to
+    from tip_b200 import synth
+    data = synth.make_tip_data(n_drug=300, n_prot=900, n_rel=48, dd_undirected=60_000, pp_undirected=5_000, pd_edges=700,
+                               seed=21)
+    n_drug, n_prot, n_rel = data["n_drug"], data["n_prot"], data["n_dd_et"]
+    gen = torch.Generator().manual_seed(5)
+    for mod, pd, ne in (("cat", 16, 48), ("add", 64, 64)):
+        f0 = pd + ne if mod == "cat" else ne
+        p = {"encoder.embed": torch.randn(n_drug, ne, generator=gen),
+             "encoder.pp_encoder.conv1.bias": torch.randn(32, generator=gen) * 0.1,
+             "encoder.pp_encoder.conv1.lin.weight": torch.randn(32, n_prot, generator=gen) * 0.05,
+             "encoder.pp_encoder.conv2.bias": torch.randn(16, generator=gen) * 0.1,
+             "encoder.pp_encoder.conv2.lin.weight": torch.randn(16, 32, generator=gen) * 0.3,
+             "encoder.hgcn.weight": torch.randn(16, pd, generator=gen) * 0.25,
+             "decoder.weight": torch.randn(n_rel, 16, generator=gen) * 0.25}
+        for name, (fi, fo, relu) in (("rgcn1", (f0, 32, False)), ("rgcn2", (32, 16, True))):
+            for k, v in to.init_rgcn_params(fi, fo, n_rel, 32, relu, gen).items():
+                p[f"encoder.{name}.{k}"] = v
+        cpu = {k: v for k, v in data.items() if torch.is_tensor(v) and not v.is_sparse}
+        neg = torch.from_numpy(nso.typed_negative_sampling(nso.MT19937(3), cpu["dd_train_idx"].numpy(), n_drug,
+                                                           cpu["dd_train_range"].numpy()))
+        results = []
+        for kw in (dict(structural=True), dict(structural=False, sparse=True)):
+            q = to.to_dtype(p, torch.float64, requires_grad=True)
+            loss, z = to.TipOracle(q, n_drug, n_prot, mod=mod, **kw).loss(cpu, neg)
+            loss.backward()
+            results.append((loss.detach(), z.detach(), {k: v.grad for k, v in q.items()}))
+        (l0, z0, g0), (l1, z1, g1) = results
+        assert len(g0) == 13
+        torch.testing.assert_close(l1, l0, rtol=1e-12, atol=0)
+        torch.testing.assert_close(z1, z0, rtol=1e-10, atol=1e-13)
+        for k in g0:
+            torch.testing.assert_close(g1[k], g0[k], rtol=1e-9, atol=1e-12 * float(g0[k].abs().max()), msg=lambda m: k + ": " + m)

@@ -80,12 +80,17 @@ def _make_small_data():
                                pd_edges=500, seed=5)
 
 
-def _gpu_worker(rank, world, port, out):
+def _bench_data():
+    import bench
+    return bench.make_data("polypharmacy")[0]       # exactly the instance bench.py times
+
+
+def _gpu_worker(rank, world, port, out, big=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tip_b200 import layers, neg_sampling as ns, parallel
     dev = torch.device("cuda:0")
-    data = _make_small_data()
+    data = _bench_data() if big else _make_small_data()
     torch.manual_seed(1111)
     ns.seed(1111, dev)
     settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
@@ -112,12 +117,14 @@ def _gpu_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_two_rank_sharding_equals_single_rank():
+@pytest.mark.parametrize("big", [False, True], ids=["small", "benched-workload"])
+def test_two_rank_sharding_equals_single_rank(big):
+    """`big`: the exact instance bench.py times (861 relations, 8.28 M edges) split over two ranks"""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     from tip_b200 import layers, neg_sampling as ns
     dev = torch.device("cuda:0")
-    data = _make_small_data()
+    data = _bench_data() if big else _make_small_data()
     torch.manual_seed(1111)
     ns.seed(1111, dev)
     settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
@@ -137,7 +144,7 @@ def test_two_rank_sharding_equals_single_rank():
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_gpu_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_gpu_worker, args=(world, _free_port(), out, big), nprocs=world, join=True)
     res = dict(out)
     assert set(res) == {0, 1}
     for rank in (0, 1):

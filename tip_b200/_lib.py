@@ -102,8 +102,19 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """raw handle of torch's current stream on `device` (default: the current device)"""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t):
+    """context: make the device of tensor/device `t` current.  The library launches on the CURRENT device (its
+    pointers must live there), so every public entry point of tip_b200 wraps its calls in this guard -- the reference
+    API selects the GPU through tensors / the `device` argument, not through torch.cuda.set_device."""
+    dev = t.device if torch.is_tensor(t) else torch.device(t)
+    if dev.type != "cuda":
+        raise TipbError("tip_b200 operators take CUDA tensors only (there is no CPU path)")
+    return torch.cuda.device(dev)
 
 
 def csr_layout(n_entries, n_nodes, n_rel):

@@ -637,11 +637,13 @@ k_materialize_exact(const int* __restrict__ A, const uint32_t* __restrict__ memb
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 k_finalize(const uint32_t* __restrict__ U, const int* __restrict__ Apos, const int* __restrict__ chain_out,
-           uint32_t* __restrict__ state) {
+           const int* __restrict__ call_status, int* __restrict__ sticky_status, uint32_t* __restrict__ state) {
     __shared__ int64_t s_flat;
     if (threadIdx.x == 0) {
+        const int failed = *call_status;
+        if (failed) atomicOr(sticky_status, failed);   // sticky: only the host clears it
         const int consumed = chain_out[0];
-        s_flat = consumed > 0 ? int64_t(Apos[consumed - 1]) + 1 : -1;
+        s_flat = (!failed && consumed > 0) ? int64_t(Apos[consumed - 1]) + 1 : -1;   // a failed call consumes nothing
     }
     __syncthreads();
     const int64_t flat = s_flat;  // index (in U) of the next unread word
@@ -687,7 +689,7 @@ k_bitmap_popcount(const uint32_t* __restrict__ member, int64_t words_per_rel, in
 static int64_t bitmap_words(int64_t n_nodes) { return (n_nodes * n_nodes + 31) / 32; }
 
 struct NegWs {
-    int *flags, *A, *Apos, *NHI, *PR, *F, *G, *off, *chain_out;
+    int *flags, *A, *Apos, *NHI, *PR, *F, *G, *off, *chain_out, *call_status;
     int *perm, *rounds, *round_ptr, *n_rounds;
     int round_cap;
     void* scan_ws;
@@ -705,6 +707,7 @@ static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t n_words, int
     t.G = c.take<int>(sum_w + 1024);
     t.off = c.take<int>(n_rel + 1);
     t.chain_out = c.take<int>(4);
+    t.call_status = c.take<int>(4);
     t.perm = c.take<int>(n_edges + 1);
     t.round_cap = int(n_rel * 8 + 65536);  // a relation whose pairs cover 99% of the cells needs ~1500 rounds
     t.rounds = c.take<int>(size_t(t.round_cap) * 2);
@@ -827,7 +830,11 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     const int64_t wpr = bitmap_words(n_nodes);
     int rc;
 
-    TIPB_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    // `status` is STICKY: failure bits of every call are OR-ed into it and only the caller clears it (after reading
+    // it on the host).  The bits of THIS call are collected in a workspace word; k_finalize folds them into `status`
+    // and leaves the MT19937 state untouched when the call failed (the caller reruns it from the same state).
+    int* call_status = w.call_status;
+    TIPB_CHECK_CUDA(cudaMemsetAsync(call_status, 0, sizeof(int32_t), s));
     const int64_t n_chunks = ceil_div(n_words, ACC_CHUNK);
     k_accept_count<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
     if ((rc = exclusive_scan_i32(w.flags, w.flags, n_chunks, w.scan_ws, s))) return rc;
@@ -836,7 +843,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     const int* n_acc = w.flags + n_chunks;
     if (exact_mode) {
         k_chain_exact<<<1, 1024, 0, s>>>(w.A, n_acc, member, wpr, range_list, (int)n_rel, w.round_cap, w.rounds,
-                                         w.round_ptr, w.n_rounds, w.chain_out, status);
+                                         w.round_ptr, w.n_rounds, w.chain_out, call_status);
         k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
     } else {
@@ -846,11 +853,11 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
             const size_t tsm = size_t(n_rel) * sizeof(int4);
             if ((rc = ensure_dyn_smem((const void*)k_chain_stitch, tsm))) return rc;
             k_chain_blocks<<<dim3(16, (unsigned)n_blocks), T, 0, s>>>(table, w.F, (int)n_rel, w.G);
-            k_chain_stitch<<<1, CHAIN_MAX_BLOCKS, tsm, s>>>(table, w.F, w.G, (int)n_rel, w.off, w.chain_out, status);
+            k_chain_stitch<<<1, CHAIN_MAX_BLOCKS, tsm, s>>>(table, w.F, w.G, (int)n_rel, w.off, w.chain_out, call_status);
         } else {
             const size_t smem = size_t(n_rel) * 20 + size_t((WALK_AHEAD + 1) * WALK_WIN + 16) * sizeof(int);
             if ((rc = ensure_dyn_smem((const void*)k_chain_walk, smem))) return rc;
-            k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, status);
+            k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, call_status);
         }
         if (n_edges > 0)
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
@@ -860,7 +867,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
                                                                             w.NHI, (int)n_rel, (int)n_nodes, n_edges,
                                                                             neg_edge_index);
     }
-    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, mt_state);
+    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, call_status, status, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");
     return TIPB_OK;
 }

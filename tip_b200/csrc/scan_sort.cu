@@ -41,9 +41,11 @@ int max_smem_optin() {
 int ensure_dyn_smem(const void* func, size_t bytes) {
     if (bytes <= 48 * 1024) return TIPB_OK;
     static std::mutex mu;
-    static std::map<const void*, size_t> granted;
+    static std::map<std::pair<int, const void*>, size_t> granted;   // the attribute is per (device, function)
+    int dev = 0;
+    TIPB_CHECK_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
-    size_t& cur = granted[func];
+    size_t& cur = granted[std::make_pair(dev, func)];
     if (cur >= bytes) return TIPB_OK;
     size_t want = size_t(max_smem_optin());
     if (bytes > want) {

@@ -9,6 +9,7 @@ Reference lines (relative to the reference root) are cited per class.
 """
 import math
 import pickle
+import weakref
 
 import numpy as np
 import torch
@@ -160,14 +161,24 @@ class GCNConv(nn.Module):
         self._cache = None
 
     def _graph(self, edge_index, n):
-        if self._cache is not None:
-            return self._cache
+        c = self._cache
+        if c is not None:
+            # PyG's cached=True keeps the normalised graph of the FIRST call whatever is passed later; so does this
+            # module -- except when that very tensor was overwritten in place since (its version counter moved):
+            # every other index structure of the package re-keys on `_version`, and so does this one.
+            if c[3]() is not edge_index or c[4] == edge_index._version:
+                return c[:3]
         plan_dst = ops.cached_plan(edge_index, n, 1, by_src=False, drop_self_loops=True)
         plan_src = ops.cached_plan(edge_index, n, 1, by_src=True, drop_self_loops=True)
         graph = (plan_dst, plan_src, ops.gcn_norm(plan_dst))
         if self.cached:
-            self._cache = graph
+            self._cache = graph + (weakref.ref(edge_index), edge_index._version)
         return graph
+
+    def __getstate__(self):      # torch.save(model) (tip.py:36): parameters travel, device-side caches do not
+        state = dict(self.__dict__)
+        state["_cache"], state["_identity_ok"] = None, {}
+        return state
 
     def _linear(self, x):
         if x.is_sparse:
@@ -351,8 +362,16 @@ class TIP(nn.Module):
             self.embeddings = self._encode()
         self.decoder = MultiInnerProductDecoder(s.n_hid2, d.n_dd_et).to(self.device)
 
+    def __getstate__(self):      # torch.save(model) (tip.py:36): streams and per-step index buffers are runtime state
+        state = dict(self.__dict__)
+        for k in ("_neg_plan", "_neg_index", "_side"):
+            state[k] = None
+        return state
+
     def invalidate_graph_caches(self):
-        """forget every cached index structure (after the graph tensors were overwritten in place)"""
+        """Kept for callers of the first release: every cached index structure (typed CSRs, GCN normalisation,
+        positive-pair bitmaps) re-keys itself on the `_version` of its graph tensors, so nothing needs to be done
+        after an in-place overwrite.  Dropping the GCN caches here only forces their rebuild."""
         self.encoder.pp_encoder.conv1._cache = None
         self.encoder.pp_encoder.conv2._cache = None
 

@@ -202,6 +202,11 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
     synchronisation (use it inside CUDA-graph capture; call `last_status()` later)."""
     if not pos_edge_index.is_cuda:
         raise _lib.TipbError("typed_negative_sampling takes CUDA tensors only (there is no CPU path)")
+    with torch.cuda.device(pos_edge_index.device):     # the library launches on the current device
+        return _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out)
+
+
+def _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out):
     assert pos_edge_index.dtype == torch.long and pos_edge_index.dim() == 2 and pos_edge_index.shape[0] == 2
     num_nodes = int(num_nodes)
     dev = pos_edge_index.device
@@ -213,22 +218,30 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
     L = lib()
     rng = _get_rng(dev)
     exact = 0
+    if check_status:
+        # the status word is sticky (the library only ORs into it): anything pending here was left by an earlier
+        # UNCHECKED call, whose negatives -- and every step since -- were therefore not the reference's
+        pending = int(m.status.item())
+        if pending:
+            m.status.zero_()
+            raise _lib.TipbError(f"negative sampling: an earlier unchecked call failed (status {pending}); its "
+                                 "negatives differ from the reference's.  Use check_status=True or call last_status()")
     while True:
         rng.join()                                   # an earlier prefetch must be done before its words are read
         if not rng.valid or rng.n_new < m.n_new:
             rng.generate(max(m.n_new, rng.n_new))    # on the caller's stream (first call / state was reset)
             rng.valid = True
-        saved = rng.state.clone() if check_status else None
         n_words = 624 + rng.n_new
         ws = workspace(L.tipb_neg_sample_workspace_bytes(m.n_edges, m.n_rel, n_words, m.sum_l, m.sum_w), dev, "neg")
         check(L.tipb_neg_sample(ptr(rng.state), ptr(rng.words), n_words, ptr(m.member), ptr(m.range_dev), ptr(m.table),
                                 m.sum_l, m.sum_w, m.n_edges, num_nodes, m.n_rel, exact, ptr(out), ptr(m.status),
                                 ptr(ws), ws.numel(), stream()), "neg_sample")
-        rng.valid = False                            # the state moved on; `words` no longer starts at it
         code = int(m.status.item()) if check_status else 0
         if code == 0:
+            rng.valid = False                        # the state moved on; `words` no longer starts at it
             break
-        rng.state.copy_(saved)                       # rewind the stream and redo this call
+        # a failed call consumed nothing (the library leaves the MT19937 state alone): rerun it from the same state
+        m.status.zero_()
         if code & 2:
             raise _lib.TipbError("negative sampling: the retry-round table overflowed "
                                  "(some relation's positive pairs cover almost every cell)")
@@ -247,14 +260,18 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=
     return out
 
 
-def last_status(device=None):
-    """OR of the status words of all cached samplers on `device` (0 = every unchecked call had enough
-    pre-generated words and stayed inside its brackets).  One host synchronisation."""
+def last_status(device=None, clear=True):
+    """OR of the sticky status words of all cached samplers on `device`: 0 = EVERY unchecked call since the last
+    read had enough pre-generated words and stayed inside its brackets.  The library only ever ORs failure bits
+    into the word and a failed call does not advance the MT19937 state, so a failure inside a CUDA-graph replay
+    cannot be overwritten by later steps.  One host synchronisation; `clear` resets the words after reading."""
     device = _device_of(device)
     code = 0
     for m in _member_cache.values():
         if m.status.device == device:
             code |= int(m.status.item())
+            if clear:
+                m.status.zero_()
     return code
 
 

@@ -5,7 +5,9 @@ are allocated with torch, raw pointers + the current CUDA stream go to the
 library.  No computation of the hot path happens in Python, and nothing falls
 back to torch ops when the library is missing (tip_b200._lib raises).
 """
+import functools
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -41,6 +43,18 @@ def _i64c(t):
     return t.contiguous()
 
 
+def _guarded(fn):
+    """run `fn` with the device of its first tensor argument current (the library launches on the current device)"""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is None or not t.is_cuda:
+            return fn(*args, **kw)          # the callee raises the "CUDA tensors only" error
+        with torch.cuda.device(t.device):
+            return fn(*args, **kw)
+    return wrapper
+
+
 def _next_pow2(v, lo=4):
     p = lo
     while p < v:
@@ -71,11 +85,12 @@ class TypedCSR(object):
         assert edge_index.dim() == 2 and edge_index.shape[0] == 2 and edge_index.shape[1] == self.n_edges
         edge_type = None if edge_type is None else _i64c(edge_type)
         range_list = None if range_list is None else _i64c(range_list.to(torch.long))
-        ws = workspace(self._ws_bytes, self.device, "csr")
-        check(lib().tipb_typed_csr_build(ptr(edge_index), ptr(edge_type), ptr(range_list), self.n_edges, self.n_nodes,
-                                         self.n_other, self.n_rel, int(self.by_src), int(self.doubled),
-                                         int(self.drop_self_loops), int(self.rel_major), ptr(self.buf), self.nbytes,
-                                         ptr(ws), ws.numel(), stream()), "typed_csr_build")
+        with torch.cuda.device(self.device):
+            ws = workspace(self._ws_bytes, self.device, "csr")
+            check(lib().tipb_typed_csr_build(ptr(edge_index), ptr(edge_type), ptr(range_list), self.n_edges,
+                                             self.n_nodes, self.n_other, self.n_rel, int(self.by_src), int(self.doubled),
+                                             int(self.drop_self_loops), int(self.rel_major), ptr(self.buf), self.nbytes,
+                                             ptr(ws), ws.numel(), stream()), "typed_csr_build")
         return self
 
     # ---- views (tests, inv_deg for the backward pass)
@@ -103,6 +118,7 @@ _plan_cache = {}
 
 def clear_plan_cache():
     _plan_cache.clear()
+    _dec_plans.clear()
 
 
 def _tensor_key(t):
@@ -177,6 +193,7 @@ class _RGCNFunction(torch.autograd.Function):
         return d_x, d_basis, d_att, d_root, None, None, None
 
 
+@_guarded
 def rgcn_conv(x, basis, att, root, plan_dst, plan_src, bias=None, relu=False):
     """out = mean-aggregated basis-decomposed relational conv + x @ root (+ bias) (+ ReLU).
     Feature widths that are not powers of two in [4,128] are zero-padded here (exact)."""
@@ -231,10 +248,12 @@ class _GCNSpmmFunction(torch.autograd.Function):
 
 def gcn_norm(plan_dst):
     dis = torch.empty(plan_dst.n_nodes, dtype=torch.float32, device=plan_dst.device)
-    check(lib().tipb_gcn_norm(ptr(plan_dst.buf), plan_dst.n_entries, plan_dst.n_nodes, ptr(dis), stream()), "gcn_norm")
+    with torch.cuda.device(plan_dst.device):
+        check(lib().tipb_gcn_norm(ptr(plan_dst.buf), plan_dst.n_entries, plan_dst.n_nodes, ptr(dis), stream()), "gcn_norm")
     return dis
 
 
+@_guarded
 def gcn_spmm(x, bias, plan_dst, plan_src, dis, relu=False):
     f = x.shape[1]
     fp = _next_pow2(f)
@@ -277,6 +296,7 @@ class _HierFunction(torch.autograd.Function):
         return d_x, d_w, None, None, None, None
 
 
+@_guarded
 def hier_conv(x, weight, plan_dst, plan_src, n_source, n_target):
     f_in, f_out = weight.shape
     fi, fo = _next_pow2(f_in), _next_pow2(f_out)
@@ -306,7 +326,7 @@ class _DecoderFunction(torch.autograd.Function):
         z, weight, edge_index, edge_type = ctx.saved_tensors
         grad_out = _f32c(grad_out)
         n_edges, n_nodes, n_rel, dim = edge_index.shape[1], z.shape[0], weight.shape[0], z.shape[1]
-        plan = cached_plan(edge_index, n_nodes, n_rel, edge_type=edge_type, validate=False, by_src=False, doubled=True, rel_major=True)
+        plan = _decoder_grad_plan(edge_index, edge_type, n_nodes, n_rel)
         L = lib()
         d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
         ws = workspace(L.tipb_decoder_workspace_bytes(n_edges, n_nodes, n_rel, dim), z.device)
@@ -315,6 +335,32 @@ class _DecoderFunction(torch.autograd.Function):
         return d_z, d_w, None, None, None
 
 
+_dec_plans = {}     # (n_edges, n_nodes, n_rel, device) -> [plan, weakref(edge_index), weakref(edge_type), versions]
+
+
+def _decoder_grad_plan(edge_index, edge_type, n_nodes, n_rel):
+    """doubled typed CSR for the decoder gradient.  The decoder is called with FRESH negatives every step
+    (src/layers.py:333-336), so these plans do not go through the identity-keyed `cached_plan` (which would pin one
+    2E-entry plan plus its edge tensors per call): ONE buffer per shape is rebuilt in place, and reused as is only
+    while the very same tensor objects (held weakly) are passed again unmodified -- the positive edges."""
+    key = (int(edge_index.shape[1]), int(n_nodes), int(n_rel), str(edge_index.device))
+    versions = _versions(edge_index, edge_type)
+    hit = _dec_plans.get(key)
+    if hit is not None and hit[1]() is edge_index and hit[2]() is edge_type and hit[3] == versions:
+        return hit[0]
+    if hit is None:
+        while len(_dec_plans) >= 4:                       # a handful of shapes (train / test, pos / neg share one)
+            _dec_plans.pop(next(iter(_dec_plans)))
+        plan = TypedCSR(edge_index.shape[1], n_nodes, n_rel, edge_index.device, by_src=False, doubled=True,
+                        rel_major=True)
+    else:
+        plan = hit[0]
+    plan.build(edge_index, edge_type)
+    _dec_plans[key] = [plan, weakref.ref(edge_index), weakref.ref(edge_type), versions]
+    return plan
+
+
+@_guarded
 def decoder_score(z, weight, edge_index, edge_type, sigmoid=True):
     dim = z.shape[1]
     dp = _next_pow2(dim)
@@ -359,6 +405,7 @@ class _BCELossFunction(torch.autograd.Function):
 _mirror_cache = {}
 
 
+@_guarded
 def edges_mirrored(edge_index, range_list):
     """True iff every relation range is [pairs..., the same pairs with rows swapped...] (src/utils.py:17-23).
     Checked on the device once per (tensor, version); one host synchronisation at that time."""
@@ -384,6 +431,7 @@ def positive_decoder_plan(edge_index, n_nodes, n_rel, range_list):
     return cached_plan(edge_index, n_nodes, n_rel, range_list=range_list, by_src=False, doubled=True, rel_major=True)
 
 
+@_guarded
 def bce_loss(z, weight, plan_pos, plan_neg, neg_stream=None):
     dim = z.shape[1]
     dp = _next_pow2(dim)
@@ -394,6 +442,7 @@ def bce_loss(z, weight, plan_pos, plan_neg, neg_stream=None):
     return _BCELossFunction.apply(z, weight, plan_pos, plan_neg, neg_stream)
 
 
+@_guarded
 def decoder_sweep(z, weight, sigmoid=True):
     z, weight = _f32c(z), _f32c(weight)
     n, dim = z.shape
@@ -412,6 +461,7 @@ def check_cumulative_ranges(range_list, n_edges):
         raise ValueError("range_list must be the cumulative [start,end) table of src/utils.py:26-32 covering every edge")
 
 
+@_guarded
 def eval_auprc_auroc_ap(pos_score, neg_score, range_list):
     """record[3, n_rel] (float64, on the device): auprc, auroc, ap per relation -- src/layers.py:353-369 without the
     861 host round trips"""
