@@ -212,8 +212,35 @@ size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n
 int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* stream_words, int64_t n_words /* 624 + n_new */,
                     const uint32_t* member, const int64_t* range_list, const int64_t* table /* device copy */,
                     int64_t sum_l, int64_t sum_w, int64_t n_edges, int64_t n_nodes, int64_t n_rel, int exact_mode,
-                    int64_t* neg_edge_index /* [2,n_edges] */, int32_t* status, void* ws, size_t ws_bytes,
-                    void* stream);
+                    int64_t* neg_edge_index /* [2,n_edges], nullable */,
+                    uint32_t* neg_packed /* [n_edges] (row << 16 | col), nullable; n_nodes <= 65535 */,
+                    int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- fused pair pass (decoder + loss + gradient)
+ * Replaces, for the training step, decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340 AND what
+ * autograd derives from them, without the typed CSR of the freshly sampled negatives: a pair (i, j, r) is scored once
+ * by one thread, the 2T pair-ends of a tile are grouped by node inside the CTA (stable, no float atomics).
+ * Usable when z (n_nodes x dim fp32) fits in shared memory: tipb_pair_pass_supported; otherwise use the
+ * tipb_decoder_bce_fused path above.
+ *   pairs    packed (row << 16 | col), all pairs of relation r contiguous
+ *   items    int32 [n_items,4] = (relation, first pair, pair count <= tipb_pair_chunk(), slot), built by the caller from
+ *            the relation ranges (static per graph), largest first; a slot receives one item's partial results
+ *   slots    the positive pass's slots come first, each pass numbers its slots relation-major;
+ *            rel_slot_ptr = int32 [2 * (n_rel + 1)]: slot ranges per relation of the positive, then the negative pass
+ *   pair_weight  multiplicity / number of scored entries: 2/E for the first halves of a mirrored edge set
+ *            (src/utils.py:17-23: every undirected pair stands for two directed entries), 1/E for negatives */
+int tipb_pair_pass_supported(int64_t n_nodes, int dim);
+int64_t tipb_pair_chunk(void);
+size_t tipb_pair_workspace_bytes(int64_t n_slots_total, int64_t n_nodes, int dim);
+int tipb_pack_half_pairs(const int64_t* edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_rel,
+                         int64_t n_nodes, uint32_t* packed /* [n_edges / 2] */, int32_t* status, void* stream);
+int tipb_unpack_pairs(const uint32_t* packed, int64_t n, int64_t* edge_index /* [2,n] */, void* stream);
+int tipb_pair_bce_pass(const uint32_t* pairs, const int32_t* items, int64_t n_items, int64_t n_slots_total,
+                       int64_t n_nodes, const float* z, const float* weight, int dim, int sign, float pair_weight,
+                       void* ws, size_t ws_bytes, void* stream);
+int tipb_pair_bce_finish(const int32_t* rel_slot_ptr, int64_t n_slots_total, int64_t n_nodes, int64_t n_rel, int dim,
+                         float* loss_out /* [1] */, float* d_z, float* d_weight, void* ws, size_t ws_bytes,
+                         void* stream);
 
 /* ---------------------------------------------------------------- per-relation evaluation
  * Replaces TIP.compute_auprc_auroc_ap_by_et / auprc_auroc_ap (src/layers.py:353-375, src/utils.py:86-93), i.e. 861

@@ -810,3 +810,81 @@ def test_benched_workload_parity(mod):
     assert len(grads) == 13
     for n_, g in grads.items():
         close(g, ref_grads[n_], what="grad " + n_)
+
+
+# =============================================================================== fused pair pass (csrc/pair_pass.cu)
+def _mirrored_graph(rng, n, sizes):
+    """relation-sorted edge set in the reference layout (src/utils.py:17-23): [pairs..., mirrored pairs...] per relation"""
+    halves, rl, et, start = [], [], [], 0
+    for rel, k in enumerate(sizes):
+        pairs = rng.integers(0, n, (2, int(k))).astype(np.int64)
+        halves.append(np.concatenate([pairs, pairs[::-1]], axis=1))
+        rl.append([start, start + 2 * int(k)])
+        et.append(np.full(2 * int(k), rel, dtype=np.int64))
+        start += 2 * int(k)
+    return np.concatenate(halves, axis=1), np.array(rl, dtype=np.int64), np.concatenate(et)
+
+
+@pytest.mark.parametrize("n,dim,sizes", [
+    (645, 16, [900, 0, 20_000, 3, 2048, 2049, 1, 700]),      # empty relation, multi-item relation, tile boundaries
+    (300, 8, [500] * 12),
+    (97, 4, [40, 0, 0, 333]),
+    (130, 32, [1500, 2500]),
+    (645, 12, [800, 1200]),                                   # width padded to 16 by the Python layer
+])
+def test_pair_pass_against_oracle(n, dim, sizes):
+    """ops.pair_bce_loss (one thread scores a pair, in-CTA grouping of the pair-ends) == the reference's loss
+    (src/layers.py:335-340) and its autograd gradient, fp64 oracle"""
+    from oracle import tip_oracle as to
+    from tip_b200 import ops
+    d = dev()
+    rng = np.random.default_rng(n + dim)
+    ei, rl, et = _mirrored_graph(rng, n, sizes)
+    e, r = ei.shape[1], len(sizes)
+    neg = rng.integers(0, n, (2, e)).astype(np.int64)
+    neg[:, :5] = neg[:, 5:10]                                 # duplicate pairs and a self pair
+    neg[1, 11] = neg[0, 11]
+    torch.manual_seed(n)
+    z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
+    ei_t, rl_t = T(ei, d), T(rl, d)
+    plan = ops.pair_plan(ei_t, n, r, rl_t, dim)
+    assert plan is not None and plan.n_edges == e
+    packed = ((T(neg[0], d) << 16) | T(neg[1], d)).to(torch.int32)
+    assert torch.equal(ops.unpack_pairs(packed).cpu(), T(neg))
+    zg, wg = z.to(d).requires_grad_(True), w.to(d).requires_grad_(True)
+    loss = ops.pair_bce_loss(zg, wg, plan, packed)
+    (loss * 1.5).backward()
+    z64, w64 = z.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = to.tip_loss(to.decoder(z64, T(ei), T(et), w64), to.decoder(z64, T(neg), T(et), w64))
+    (ref * 1.5).backward()
+    close(loss, ref, rtol=1e-5, what="loss")
+    close(zg.grad, z64.grad, what="dz")
+    close(wg.grad, w64.grad, what="dw")
+    # run-to-run deterministic (no float atomics: every sum has one fixed order)
+    zg2, wg2 = z.to(d).requires_grad_(True), w.to(d).requires_grad_(True)
+    loss2 = ops.pair_bce_loss(zg2, wg2, plan, packed)
+    (loss2 * 1.5).backward()
+    assert torch.equal(loss2, loss) and torch.equal(zg2.grad, zg.grad) and torch.equal(wg2.grad, wg.grad)
+    # the general typed-CSR path gives the same numbers
+    plan_neg = ops.TypedCSR(e, n, r, d, doubled=True, rel_major=True).build(T(neg, d), range_list=rl_t)
+    zg3, wg3 = z.to(d).requires_grad_(True), w.to(d).requires_grad_(True)
+    loss3 = ops.bce_loss(zg3, wg3, ops.positive_decoder_plan(ei_t, n, r, rl_t), plan_neg)
+    (loss3 * 1.5).backward()
+    close(loss3, loss, rtol=1e-5, what="loss (two paths)")
+    close(zg3.grad, zg.grad, what="dz (two paths)")
+    close(wg3.grad, wg.grad, what="dw (two paths)")
+
+
+def test_pair_pass_applicability():
+    from tip_b200 import _lib, ops
+    d = dev()
+    L = _lib.lib()
+    assert L.tipb_pair_pass_supported(645, 16) == 1 and L.tipb_pair_pass_supported(1024, 16) == 1
+    assert L.tipb_pair_pass_supported(10_000, 16) == 0          # z does not fit in shared memory: typed-CSR path
+    assert L.tipb_pair_pass_supported(645, 12) == 0             # widths are padded to a power of two by the caller
+    rng = np.random.default_rng(0)
+    ei, rl, _ = _mirrored_graph(rng, 50, [30, 40])
+    broken = ei.copy()
+    broken[0, 3] = (broken[0, 3] + 1) % 50
+    assert ops.pair_plan(T(broken, d), 50, 2, T(rl, d), 16) is None      # not mirrored: general path
+    assert ops.pair_plan(T(ei, d), 50, 2, T(rl, d), 16) is not None

@@ -47,7 +47,14 @@ SIGNATURES = {
     "tipb_neg_bitmap_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "tipb_neg_table_build": (C.c_int, [_p, _p, _i64, _i64, C.c_double, _p, _p]),
     "tipb_neg_sample_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i64]),
-    "tipb_neg_sample": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_neg_sample": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "tipb_pair_pass_supported": (C.c_int, [_i64, _i32]),
+    "tipb_pair_chunk": (_i64, []),
+    "tipb_pair_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "tipb_pack_half_pairs": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "tipb_unpack_pairs": (C.c_int, [_p, _i64, _p, _p]),
+    "tipb_pair_bce_pass": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i32, C.c_float, _p, _sz, _p]),
+    "tipb_pair_bce_finish": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "tipb_eval_workspace_bytes": (_sz, [_i64, _i64]),
     "tipb_eval_auprc_auroc_ap": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "tipb_adam_max_tensors": (C.c_int, []),

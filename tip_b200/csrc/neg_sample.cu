@@ -173,11 +173,18 @@ __device__ __forceinline__ bool is_member(const uint32_t* __restrict__ bits, int
     return (bits[key >> 5] >> (key & 31)) & 1u;
 }
 
-__device__ __forceinline__ void write_pair(int64_t* __restrict__ out, int64_t n_edges, int64_t e, int p, int n_nodes,
-                                           float fn) {
+// `out` = the reference's int64 [2, n_edges] (may be NULL), `packed` = (row << 16 | col) per pair (may be NULL; the
+// fused training step consumes this form, csrc/pair_pass.cu)
+__device__ __forceinline__ void write_pair(int64_t* __restrict__ out, uint32_t* __restrict__ packed, int64_t n_edges,
+                                           int64_t e, int p, int n_nodes, float fn) {
     const float row = __fdiv_rn(__int2float_rn(p), fn);  // float32 true division, as torch does for perm / N
-    out[e] = (long long)row;                             // .long(): truncation toward zero
-    out[n_edges + e] = (long long)(p % n_nodes);
+    const long long r = (long long)row;                  // .long(): truncation toward zero
+    const int c = p % n_nodes;
+    if (out) {
+        out[e] = r;
+        out[n_edges + e] = (long long)c;
+    }
+    if (packed) packed[e] = (uint32_t(r) << 16) | uint32_t(c);
 }
 
 // ================================================================================================
@@ -462,15 +469,24 @@ __global__ void __launch_bounds__(256)
 k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                    const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                    const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
-                   int64_t* __restrict__ out) {
-    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
-    int lo_r = 0, hi_r = n_rel - 1;
-    while (lo_r < hi_r) {
-        int mid = (lo_r + hi_r + 1) >> 1;
-        if (range_list[2 * mid] <= e) lo_r = mid; else hi_r = mid - 1;
+                   int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
+    // the block's 256 consecutive draws span very few relations: one thread finds the relation of the first draw
+    // (binary search), every thread then walks forward from it
+    __shared__ int s_first;
+    const int64_t e0 = int64_t(blockIdx.x) * blockDim.x;
+    if (threadIdx.x == 0) {
+        int lo_r = 0, hi_r = n_rel - 1;
+        while (lo_r < hi_r) {
+            int mid = (lo_r + hi_r + 1) >> 1;
+            if (range_list[2 * mid] <= e0) lo_r = mid; else hi_r = mid - 1;
+        }
+        s_first = lo_r;
     }
-    const int r = lo_r;
+    __syncthreads();
+    const int64_t e = e0 + threadIdx.x;
+    if (e >= n_edges) return;
+    int r = s_first;
+    while (r + 1 < n_rel && range_list[2 * (r + 1)] <= e) ++r;
     const int64_t start = range_list[2 * r];
     if (e >= range_list[2 * r + 1]) return;
     const int o = off[r];
@@ -487,7 +503,7 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
         const int hits_incl = (i + 1) - (nhi[x0 + i] - rb);
         p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
     }
-    write_pair(out, n_edges, e, p, n_nodes, float(n_nodes));
+    write_pair(out, packed, n_edges, e, p, n_nodes, float(n_nodes));
 }
 
 // rounds >= 2, one CTA per relation
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(256)
 k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                     const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                     const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
-                    int64_t* __restrict__ out) {
+                    int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
     const int r = blockIdx.x;
     if (r >= n_rel) return;
     const int o = off[r];
@@ -519,7 +535,7 @@ k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ memb
         for (int p = threadIdx.x; p < c_prev; p += blockDim.x) {
             if (is_member(bits, A[s_prev + p])) {
                 const int t = (p + 1) - (nhi[xs + p] - nb) - 1;
-                write_pair(out, n_edges, start + p, A[s_cur + t], n_nodes, fn);  // perm[rest] = tmp; rest indexes tmp_{q-1}
+                write_pair(out, packed, n_edges, start + p, A[s_cur + t], n_nodes, fn);  // perm[rest] = tmp; rest indexes tmp_{q-1}
             }
         }
         const int c = c_prev - (nhi[xs + c_prev - 1] - nb);
@@ -585,7 +601,7 @@ __global__ void __launch_bounds__(256)
 k_materialize_exact(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                     const int64_t* __restrict__ range_list, const int* __restrict__ rounds,
                     const int* __restrict__ round_ptr, const int* __restrict__ n_rounds, int n_nodes, int64_t n_edges,
-                    int* __restrict__ perm, int64_t* __restrict__ out) {
+                    int* __restrict__ perm, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
     __shared__ int sw[33];
     __shared__ int s_carry;
     const int r = blockIdx.x;
@@ -631,7 +647,7 @@ k_materialize_exact(const int* __restrict__ A, const uint32_t* __restrict__ memb
     }
     __syncthreads();
     const float fn = float(n_nodes);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) write_pair(out, n_edges, start + i, pr[i], n_nodes, fn);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) write_pair(out, packed, n_edges, start + i, pr[i], n_nodes, fn);
 }
 
 // ================================================================================================
@@ -809,10 +825,11 @@ size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n
 
 int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words, const uint32_t* member,
                     const int64_t* range_list, const int64_t* table, int64_t sum_l, int64_t sum_w, int64_t n_edges,
-                    int64_t n_nodes, int64_t n_rel, int exact_mode, int64_t* neg_edge_index, int32_t* status, void* ws,
-                    size_t ws_bytes, void* stream) {
-    TIPB_CHECK_ARG(mt_state && stream_words && member && range_list && neg_edge_index && status && ws,
+                    int64_t n_nodes, int64_t n_rel, int exact_mode, int64_t* neg_edge_index, uint32_t* neg_packed,
+                    int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(mt_state && stream_words && member && range_list && (neg_edge_index || neg_packed) && status && ws,
                    "neg_sample: NULL argument");
+    TIPB_CHECK_ARG(!neg_packed || n_nodes <= 65535, "neg_sample: the packed output holds 16-bit node ids");
     TIPB_CHECK_ARG(exact_mode || table, "neg_sample: the fast path needs the bracket table");
     TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample: n_nodes must be in [2, 46340]");
     TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample: bad stream length");
@@ -845,7 +862,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         k_chain_exact<<<1, 1024, 0, s>>>(w.A, n_acc, member, wpr, range_list, (int)n_rel, w.round_cap, w.rounds,
                                          w.round_ptr, w.n_rounds, w.chain_out, call_status);
         k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
-                                                            w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index);
+                                                            w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index, neg_packed);
     } else {
         k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
         const int n_blocks = int(ceil_div(n_rel, CHAIN_BLOCK));
@@ -862,10 +879,10 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         if (n_edges > 0)
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,
-                                                                           neg_edge_index);
+                                                                           neg_edge_index, neg_packed);
         k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                             w.NHI, (int)n_rel, (int)n_nodes, n_edges,
-                                                                            neg_edge_index);
+                                                                            neg_edge_index, neg_packed);
     }
     k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, call_status, status, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");

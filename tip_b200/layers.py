@@ -27,6 +27,7 @@ from .utils import is_sparse_identity, process_edges
 torch.manual_seed(1111)   # src/layers.py:13
 np.random.seed(1111)      # src/layers.py:14 (the device stream is seeded 1111 too, see neg_sampling._state)
 EPS = 1e-13               # src/layers.py:15
+SERIAL_STREAMS = False    # measurement aid (bench.py): keep every kernel of a step on the caller's stream
 
 
 def _require_cuda(t, who):
@@ -334,7 +335,9 @@ class TIP(nn.Module):
         self.data = self._prepare_data(data_path, settings.sp_rate, data)
         self._prepare_model()
         self._neg_plan = None
-        self._neg_index = None
+        self._neg_index_buf = None
+        self._neg_packed = None
+        self._side = None
 
     def _prepare_data(self, data_path, sp_rate, data_dict):
         if data_dict is None:
@@ -364,9 +367,21 @@ class TIP(nn.Module):
 
     def __getstate__(self):      # torch.save(model) (tip.py:36): streams and per-step index buffers are runtime state
         state = dict(self.__dict__)
-        for k in ("_neg_plan", "_neg_index", "_side"):
+        for k in ("_neg_plan", "_neg_index_buf", "_neg_packed", "_side"):
             state[k] = None
         return state
+
+    @property
+    def _neg_index(self):
+        """the last step's negative pairs as the reference has them: int64 [2, E].  The fused step keeps them packed
+        (row << 16 | col); they are unpacked here on demand (inspection / tests, not on the training path)."""
+        if self._neg_packed is not None:
+            return ops.unpack_pairs(self._neg_packed)
+        return self._neg_index_buf
+
+    @_neg_index.setter
+    def _neg_index(self, value):
+        self._neg_index_buf = value
 
     def invalidate_graph_caches(self):
         """Kept for callers of the first release: every cached index structure (typed CSRs, GCN normalisation,
@@ -382,23 +397,37 @@ class TIP(nn.Module):
 
     def forward(self, check_status=True):
         d = self.data
-        if self._neg_index is None:
-            self._neg_index = torch.empty_like(d.dd_train_idx)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # the sampler is the critical chain
+        cur = torch.cuda.current_stream(self.device)
+        side = cur if SERIAL_STREAMS else self._side
+        # ---- fused pair pass (csrc/pair_pass.cu): mirrored edge set + z fits in shared memory (the polypharmacy shape)
+        plan = ops.pair_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, d.dd_train_range, self.settings.n_hid2)
+        if plan is not None:
+            if self._neg_packed is None or self._neg_packed.numel() != d.dd_train_idx.shape[1]:
+                self._neg_packed = torch.empty(d.dd_train_idx.shape[1], dtype=torch.int32, device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):    # the negatives do not depend on the encoder: sample them meanwhile
+                typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range, check_status=check_status,
+                                        packed_out=self._neg_packed)
+            self.embeddings = self._encode()
+            return ops.pair_bce_loss(self.embeddings, self.decoder.weight, plan, self._neg_packed, neg_stream=side)
+        # ---- general path: typed CSR of the fresh negatives + segment decoder (large graphs, unmirrored edge sets)
+        self._neg_packed = None
+        if self._neg_index_buf is None or self._neg_plan is None:
+            self._neg_index_buf = torch.empty_like(d.dd_train_idx)
             self._neg_plan = ops.TypedCSR(d.dd_train_idx.shape[1], d.n_drug, d.n_dd_et, self.device, by_src=False,
                                           doubled=True, rel_major=True)
-            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # sampler -> plan is the critical chain
-        # the negatives do not depend on the encoder: sample and index them on a side stream meanwhile
-        cur = torch.cuda.current_stream(self.device)
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
             neg_index = typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range,
-                                                check_status=check_status, out=self._neg_index)
+                                                check_status=check_status, out=self._neg_index_buf)
             self._neg_plan.build(neg_index, range_list=d.dd_train_range)
         self.embeddings = self._encode()
         pos_plan = ops.positive_decoder_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, d.dd_train_range)
         # decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340, fused with their gradient;
         # only the negative pass waits for the side stream
-        return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan, neg_stream=self._side)
+        return ops.bce_loss(self.embeddings, self.decoder.weight, pos_plan, self._neg_plan, neg_stream=side)
 
     def pred(self, dd_idx, dd_et):
         return self.decoder(self.embeddings, dd_idx, dd_et)

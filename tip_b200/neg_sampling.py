@@ -197,24 +197,31 @@ def _membership(pos_edge_index, num_nodes, range_list):
     return m
 
 
-def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=True, out=None):
+def typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status=True, out=None, packed_out=None):
     """src/neg_sampling.py:22-26 on the GPU.  `check_status=False` skips the one host
-    synchronisation (use it inside CUDA-graph capture; call `last_status()` later)."""
+    synchronisation (use it inside CUDA-graph capture; call `last_status()` later).
+    `packed_out` (int32 [E], optional): the same pairs as (row << 16 | col), the form the fused training step
+    consumes (ops.pair_bce_loss); when it is given and `out` is not, the int64 [2, E] tensor is not materialised and
+    `packed_out` is returned."""
     if not pos_edge_index.is_cuda:
         raise _lib.TipbError("typed_negative_sampling takes CUDA tensors only (there is no CPU path)")
     with torch.cuda.device(pos_edge_index.device):     # the library launches on the current device
-        return _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out)
+        return _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out, packed_out)
 
 
-def _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out):
+def _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status, out, packed_out):
     assert pos_edge_index.dtype == torch.long and pos_edge_index.dim() == 2 and pos_edge_index.shape[0] == 2
     num_nodes = int(num_nodes)
     dev = pos_edge_index.device
     m = _membership(pos_edge_index, num_nodes, range_list)
-    if out is None:
+    if packed_out is not None:
+        assert packed_out.dtype == torch.int32 and packed_out.numel() == m.n_edges and packed_out.is_contiguous()
+        if num_nodes > 65535:
+            raise _lib.TipbError("packed negative pairs hold 16-bit node ids")
+    elif out is None:
         out = torch.empty((2, m.n_edges), dtype=torch.long, device=dev)
     if m.n_edges == 0:
-        return out
+        return out if out is not None else packed_out
     L = lib()
     rng = _get_rng(dev)
     exact = 0
@@ -234,8 +241,8 @@ def _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status
         n_words = 624 + rng.n_new
         ws = workspace(L.tipb_neg_sample_workspace_bytes(m.n_edges, m.n_rel, n_words, m.sum_l, m.sum_w), dev, "neg")
         check(L.tipb_neg_sample(ptr(rng.state), ptr(rng.words), n_words, ptr(m.member), ptr(m.range_dev), ptr(m.table),
-                                m.sum_l, m.sum_w, m.n_edges, num_nodes, m.n_rel, exact, ptr(out), ptr(m.status),
-                                ptr(ws), ws.numel(), stream()), "neg_sample")
+                                m.sum_l, m.sum_w, m.n_edges, num_nodes, m.n_rel, exact, ptr(out), ptr(packed_out),
+                                ptr(m.status), ptr(ws), ws.numel(), stream()), "neg_sample")
         code = int(m.status.item()) if check_status else 0
         if code == 0:
             rng.valid = False                        # the state moved on; `words` no longer starts at it
@@ -257,7 +264,7 @@ def _typed_negative_sampling(pos_edge_index, num_nodes, range_list, check_status
             rng.generate(max(m.n_new, rng.n_new))
         rng.valid = True
         rng.forked = True
-    return out
+    return out if out is not None else packed_out
 
 
 def last_status(device=None, clear=True):

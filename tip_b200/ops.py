@@ -119,6 +119,8 @@ _plan_cache = {}
 def clear_plan_cache():
     _plan_cache.clear()
     _dec_plans.clear()
+    _pair_plans.clear()
+    _mirror_cache.clear()
 
 
 def _tensor_key(t):
@@ -440,6 +442,130 @@ def bce_loss(z, weight, plan_pos, plan_neg, neg_stream=None):
     if dp != dim:
         z, weight = F.pad(z, (0, dp - dim)), F.pad(weight, (0, dp - dim))
     return _BCELossFunction.apply(z, weight, plan_pos, plan_neg, neg_stream)
+
+
+# ----------------------------------------------------------------------------- fused pair pass
+def _pair_items(ranges, chunk, slot_base):
+    """work items (relation, first pair, pair count, slot) of one pass: every relation's pairs [start, end) cut into
+    near-equal chunks of at most `chunk` pairs; slots numbered relation-major from `slot_base`; rows ordered largest
+    first (the launch order).  -> (items int32 [n,4], rel_slot_ptr int32 [n_rel+1] absolute, n_slots)"""
+    rows, ptr_ = [], [slot_base]
+    slot = slot_base
+    for r, (a, b) in enumerate(ranges):
+        a, b = int(a), int(b)
+        n = b - a
+        if n > 0:
+            k = -(-n // chunk)
+            base, extra = divmod(n, k)
+            start = a
+            for c in range(k):
+                cnt = base + (1 if c < extra else 0)
+                rows.append((r, start, cnt, slot))
+                start += cnt
+                slot += 1
+        ptr_.append(slot)
+    items = np.asarray(rows, dtype=np.int32).reshape(-1, 4)
+    order = np.argsort(-items[:, 2], kind="stable") if len(rows) else np.zeros(0, dtype=np.int64)
+    return np.ascontiguousarray(items[order]), np.asarray(ptr_, dtype=np.int32), slot - slot_base
+
+
+class PairPlan(object):
+    """Static tables of the fused pair pass (csrc/pair_pass.cu) for one mirrored, relation-sorted edge set: the
+    positive pairs (first half of every relation range, packed), the work items of the positive and the negative
+    pass, and their relation-major slot ranges.  Built once per graph (one small host copy of range_list)."""
+
+    def __init__(self, edge_index, n_nodes, n_rel, range_list):
+        L = lib()
+        dev = edge_index.device
+        self.device, self.n_nodes, self.n_rel = dev, int(n_nodes), int(n_rel)
+        self.n_edges = int(edge_index.shape[1])
+        rl_dev = _i64c(range_list.to(device=dev, dtype=torch.long))
+        rl = rl_dev.cpu().numpy()
+        check_cumulative_ranges(rl, self.n_edges)
+        chunk = int(L.tipb_pair_chunk())
+        items_pos, ptr_pos, n_pos = _pair_items(rl // 2, chunk, 0)
+        items_neg, ptr_neg, n_neg = _pair_items(rl, chunk, n_pos)
+        self.n_slots = n_pos + n_neg
+        self.n_items_pos, self.n_items_neg = int(items_pos.shape[0]), int(items_neg.shape[0])
+        self.items_pos = torch.from_numpy(items_pos).to(dev)
+        self.items_neg = torch.from_numpy(items_neg).to(dev)
+        self.rel_slot_ptr = torch.from_numpy(np.concatenate([ptr_pos, ptr_neg])).to(dev)
+        self.pos_packed = torch.empty(max(self.n_edges // 2, 1), dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.tipb_pack_half_pairs(ptr(_i64c(edge_index)), ptr(rl_dev), self.n_edges, self.n_rel, self.n_nodes,
+                                         ptr(self.pos_packed), ptr(status), stream()), "pack_half_pairs")
+        if int(status.item()) != 0:
+            raise IndexError("edge_index contains an out-of-range node id")
+
+
+_pair_plans = {}
+
+
+def pair_plan(edge_index, n_nodes, n_rel, range_list, dim):
+    """the PairPlan of a graph, or None when the fused pair pass does not apply: the edge set must be mirrored
+    (src/utils.py:17-23) and z (n_nodes x dim, dim padded to a power of two) must fit in shared memory"""
+    if not lib().tipb_pair_pass_supported(int(n_nodes), _next_pow2(int(dim))):
+        return None
+    if not edges_mirrored(edge_index, range_list):
+        return None
+    key = (_tensor_key(edge_index), _tensor_key(range_list), int(n_nodes), int(n_rel))
+    versions = _versions(edge_index, range_list)
+    hit = _pair_plans.get(key)
+    if hit is None or hit[0] != versions:
+        if len(_pair_plans) > 8:
+            _pair_plans.clear()
+        hit = _pair_plans[key] = (versions, PairPlan(edge_index, n_nodes, n_rel, range_list), (edge_index, range_list))
+    return hit[1]
+
+
+class _PairBCEFunction(torch.autograd.Function):
+    """loss = -mean(log(sig(pos)+eps)) - mean(log(1-sig(neg)+eps)) over packed pairs; gradient computed in forward"""
+
+    @staticmethod
+    def forward(ctx, z, weight, plan, neg_packed, neg_stream=None):
+        z, weight = _f32c(z), _f32c(weight)
+        n_nodes, dim = z.shape
+        n_rel = weight.shape[0]
+        assert n_nodes == plan.n_nodes and n_rel == plan.n_rel and neg_packed.numel() == plan.n_edges
+        L = lib()
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+        d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
+        ws = workspace(L.tipb_pair_workspace_bytes(plan.n_slots, n_nodes, dim), z.device, "pair")
+        e = float(max(plan.n_edges, 1))
+        check(L.tipb_pair_bce_pass(ptr(plan.pos_packed), ptr(plan.items_pos), plan.n_items_pos, plan.n_slots, n_nodes, ptr(z),
+                                   ptr(weight), dim, 1, 2.0 / e, ptr(ws), ws.numel(), stream()), "pair_bce_pass(pos)")
+        if neg_stream is not None:      # the negatives are sampled on a side stream; the positive pass did not need them
+            torch.cuda.current_stream(z.device).wait_stream(neg_stream)
+        check(L.tipb_pair_bce_pass(ptr(neg_packed), ptr(plan.items_neg), plan.n_items_neg, plan.n_slots, n_nodes, ptr(z),
+                                   ptr(weight), dim, -1, 1.0 / e, ptr(ws), ws.numel(), stream()), "pair_bce_pass(neg)")
+        check(L.tipb_pair_bce_finish(ptr(plan.rel_slot_ptr), plan.n_slots, n_nodes, n_rel, dim, ptr(loss), ptr(d_z), ptr(d_w),
+                                     ptr(ws), ws.numel(), stream()), "pair_bce_finish")
+        ctx.save_for_backward(d_z, d_w)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        d_z, d_w = ctx.saved_tensors
+        return d_z * grad_loss, d_w * grad_loss, None, None, None
+
+
+@_guarded
+def pair_bce_loss(z, weight, plan, neg_packed, neg_stream=None):
+    """TIP.forward's loss (src/layers.py:335-340) and its gradient through the fused pair pass"""
+    dim = z.shape[1]
+    dp = _next_pow2(dim)
+    if dp != dim:
+        z, weight = F.pad(z, (0, dp - dim)), F.pad(weight, (0, dp - dim))
+    return _PairBCEFunction.apply(z, weight, plan, neg_packed, neg_stream)
+
+
+def unpack_pairs(packed):
+    """packed (row << 16 | col) int32 [n] -> int64 [2, n], the reference's LongTensor layout"""
+    out = torch.empty((2, packed.numel()), dtype=torch.long, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(lib().tipb_unpack_pairs(ptr(packed), packed.numel(), ptr(out), stream()), "unpack_pairs")
+    return out
 
 
 @_guarded
