@@ -845,7 +845,9 @@ def test_pair_pass_against_oracle(n, dim, sizes):
     neg[:, :5] = neg[:, 5:10]                                 # duplicate pairs and a self pair
     neg[1, 11] = neg[0, 11]
     torch.manual_seed(n)
-    z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
+    # |value| stays below ~6: 1 - sigmoid(v) does not round to 0 in fp32 (that regime -- where the reference's own fp32
+    # arithmetic and an fp64 evaluation part ways -- is pinned separately, see the saturated case of test_bce_loss_*)
+    z, w = torch.randn(n, dim) * 0.6, torch.randn(r, dim) * 0.5
     ei_t, rl_t = T(ei, d), T(rl, d)
     plan = ops.pair_plan(ei_t, n, r, rl_t, dim)
     assert plan is not None and plan.n_edges == e

@@ -34,6 +34,7 @@ void set_last_error(const char* fmt, ...);
         cudaError_t e__ = (expr);                                                          \
         if (e__ != cudaSuccess) {                                                          \
             tipb::set_last_error("%s failed: %s", #expr, cudaGetErrorString(e__));         \
+            (void)cudaGetLastError(); /* do not leave it for the next launch check */      \
             return TIPB_ERR_CUDA;                                                          \
         }                                                                                  \
     } while (0)

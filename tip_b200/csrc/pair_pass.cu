@@ -38,23 +38,38 @@ __device__ __forceinline__ int zswz(int row, int q) {
     return row * Q + (Q >= 4 ? (q ^ ((row >> 1) & 3)) : q);
 }
 
-template <int DIM, int MODE, int OWN>
-__global__ void __launch_bounds__(PP_THREADS, 2)
-k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, int n_nodes, int key_bits,
+// one ranking round: among the 32 lanes of a warp, `peers` = lanes holding the same KB-bit key (valid lanes only)
+template <int KB>
+__device__ __forceinline__ unsigned same_key_lanes(int key, bool valid) {
+    unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int b = 0; b < KB; ++b) {
+        const unsigned bit = (unsigned(key) >> b) & 1u;
+        const unsigned m = __ballot_sync(FULL, bit != 0u);
+        peers &= ~(m ^ (0u - bit));            // keep the lanes whose bit b equals mine
+    }
+    return peers;
+}
+
+template <int DIM, int MODE, int NPT, int KB>
+__global__ void __launch_bounds__(PP_THREADS, DIM >= 32 ? 1 : 2)
+k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, int n_nodes,
             const float4* __restrict__ z, const float4* __restrict__ w, float pair_weight,
             float4* __restrict__ wacc, float4* __restrict__ zacc, float* __restrict__ loss_part) {
     constexpr int Q = DIM / 4;
     extern __shared__ float4 pp_smem[];
     float4* zs = pp_smem;                                              // [n_nodes * Q], swizzled
-    uint32_t* pk = reinterpret_cast<uint32_t*>(zs + size_t(n_nodes) * Q);   // [T] packed (row << 16 | col)
+    float4* acc2 = zs + size_t(n_nodes) * Q;                           // [(n_nodes - THREADS) * Q] rows of the nodes >= THREADS
+    const int n_hi = NPT > 1 ? max(n_nodes - PP_THREADS, 0) : 0;
+    uint32_t* pk = reinterpret_cast<uint32_t*>(acc2 + size_t(n_hi) * Q);    // [T] packed (row << 16 | col)
     float* gb = reinterpret_cast<float*>(pk + PP_T);                   // [T] d(loss)/d(value) of the pair
     uint32_t* lists = reinterpret_cast<uint32_t*>(gb + PP_T);          // [2T] (other << 16 | t), grouped by node
     int* lstart = reinterpret_cast<int*>(lists + PP_E);                // [n_nodes + 1] group offsets of this tile
-    uint16_t* wh = reinterpret_cast<uint16_t*>(lstart + n_nodes + 1);  // [WARPS][n_nodes]
+    uint16_t* wh = reinterpret_cast<uint16_t*>(lstart + ((n_nodes + 1 + 3) & ~3));   // [WARPS][n_nodes], 16-byte aligned
     __shared__ int s_scan[PP_WARPS + 1];
     __shared__ float s_loss[PP_WARPS];
     __shared__ float4 s_zacc[PP_WARPS][Q];
-    __shared__ float4 s_w[Q];                  // w[rel]: read as a broadcast (keeps 4 Q registers free for acc[])
+    __shared__ float4 s_w[Q];                  // w[rel]: read as a broadcast
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -62,24 +77,26 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
     const int rel = item.x, p0 = item.y, np = item.z, slot = item.w;
 
     for (int i = tid; i < n_nodes * Q; i += PP_THREADS) zs[zswz<Q>(i / Q, i % Q)] = z[i];
+    for (int i = tid; i < n_hi * Q; i += PP_THREADS) acc2[i] = f4_zero();
     if (tid < Q) s_w[tid] = w[size_t(rel) * Q + tid];
 
-    // accumulators of the (node, float4 column) cells this thread owns: cell c = tid + o * THREADS
-    float4 acc[OWN];
+    // thread t owns the accumulator row of node t (registers) and of node t + THREADS (shared memory, NPT == 2)
+    float4 acc[Q];
 #pragma unroll
-    for (int o = 0; o < OWN; ++o) acc[o] = f4_zero();
+    for (int q = 0; q < Q; ++q) acc[q] = f4_zero();
     float loss = 0.f;
     uint16_t* mywh = wh + wid * n_nodes;
     const int per = (n_nodes + PP_THREADS - 1) / PP_THREADS;   // nodes per thread in the scan
+    const int wh_vec = (PP_WARPS * n_nodes * 2 + 15) / 16;     // uint4 words of wh
 
     for (int t0 = 0; t0 < np; t0 += PP_T) {
         const int nt = min(PP_T, np - t0);
         __syncthreads();                       // previous tile fully consumed (and zs staged, first trip)
         for (int t = tid; t < nt; t += PP_THREADS) pk[t] = pairs[size_t(p0) + t0 + t];
-        for (int i = tid; i < (PP_WARPS * n_nodes + 1) / 2; i += PP_THREADS) reinterpret_cast<uint32_t*>(wh)[i] = 0u;
+        for (int i = tid; i < wh_vec; i += PP_THREADS) reinterpret_cast<uint4*>(wh)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
 
-        // ---- phase 1: one thread scores one pair (all operands in shared memory / registers, no shuffles)
+        // ---- phase 1: one thread scores one pair (all operands in shared memory, no shuffles)
         for (int t = tid; t < nt; t += PP_THREADS) {
             const uint32_t p = pk[t];
             const int i = int(p >> 16), j = int(p & 0xffffu);
@@ -109,16 +126,8 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
             const int t = e & (PP_T - 1);
             const bool valid = t < nt;
             const uint32_t p = pk[valid ? t : 0];
-            const int node = valid ? int(e < PP_T ? (p >> 16) : (p & 0xffffu)) : int(PP_INVALID);
-            unsigned peers = __ballot_sync(FULL, valid);
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                if (b < key_bits) {
-                    const bool bit = (node >> b) & 1;
-                    const unsigned m = __ballot_sync(FULL, bit);
-                    peers &= bit ? m : ~m;
-                }
-            }
+            const int node = int(e < PP_T ? (p >> 16) : (p & 0xffffu));
+            const unsigned peers = same_key_lanes<KB>(node, valid);
             int c0 = 0;
             if (valid) c0 = mywh[node];
             __syncwarp();
@@ -152,14 +161,16 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
         }
         if (lane == 31) s_scan[wid] = incl;
         __syncthreads();
-        if (tid == 0) {
-            int run = 0;
-            for (int ww = 0; ww < PP_WARPS; ++ww) {
-                const int c = s_scan[ww];
-                s_scan[ww] = run;
-                run += c;
+        if (wid == 0) {                        // exclusive scan of the 16 warp totals by one warp
+            const int c = lane < PP_WARPS ? s_scan[lane] : 0;
+            int x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, o);
+                if (lane >= o) x += y;
             }
-            s_scan[PP_WARPS] = run;
+            if (lane < PP_WARPS) s_scan[lane] = x - c;
+            if (lane == PP_WARPS - 1) s_scan[PP_WARPS] = x;
         }
         __syncthreads();
         int ls = s_scan[wid] + incl - mine;
@@ -189,45 +200,73 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
         }
         __syncthreads();
 
-        // ---- phase 2: every (node, column) cell adds its group, in list order
+        // ---- phase 2: every node's accumulator row adds its group, in list order (one thread per node: a full row
+        // per entry costs 2 index loads + Q row loads for 2 Q packed FMAs)
+        if (tid < n_nodes) {
+            const int end = lstart[tid + 1];
+            for (int idx = lstart[tid]; idx < end; ++idx) {
+                const uint32_t en = lists[idx];
+                const float g = gb[en & 0xffffu];
+                const int o = int(en >> 16);
 #pragma unroll
-        for (int o = 0; o < OWN; ++o) {
-            const int c = tid + o * PP_THREADS;
-            if (c < n_nodes * Q) {
-                const int n = c / Q, q = c % Q;
-                const int beg = lstart[n], end = lstart[n + 1];
-                float4 a = acc[o];
-                for (int idx = beg; idx < end; ++idx) {
-                    const uint32_t en = lists[idx];
-                    a = f4_fma(gb[en & 0xffffu], zs[zswz<Q>(int(en >> 16), q)], a);
-                }
-                acc[o] = a;
+                for (int q = 0; q < Q; ++q) acc[q] = f4_fma(g, zs[zswz<Q>(o, q)], acc[q]);
             }
+        }
+        if (NPT > 1 && tid < n_hi) {
+            const int n = tid + PP_THREADS;
+            float4 a[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) a[q] = acc2[tid * Q + q];
+            const int end = lstart[n + 1];
+            for (int idx = lstart[n]; idx < end; ++idx) {
+                const uint32_t en = lists[idx];
+                const float g = gb[en & 0xffffu];
+                const int o = int(en >> 16);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) a[q] = f4_fma(g, zs[zswz<Q>(o, q)], a[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc2[tid * Q + q] = a[q];
         }
     }
 
     // ---- item epilogue: wacc[slot] = w_r * acc, zacc[slot] = sum_n z[n] * acc[n], loss partial (fixed orders)
-    float4 zsum = f4_zero();
-    const int myq = tid % Q;                   // THREADS % Q == 0: a thread's cells all share one column
+    float4 zsum[Q];
 #pragma unroll
-    for (int o = 0; o < OWN; ++o) {
-        const int c = tid + o * PP_THREADS;
-        if (c < n_nodes * Q) {
-            wacc[size_t(slot) * n_nodes * Q + c] = f4_mul(acc[o], s_w[myq]);
-            zsum = f4_add(zsum, f4_mul(acc[o], zs[zswz<Q>(c / Q, myq)]));
+    for (int q = 0; q < Q; ++q) zsum[q] = f4_zero();
+    float4* wout = wacc + size_t(slot) * n_nodes * Q;
+    if (tid < n_nodes) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            wout[tid * Q + q] = f4_mul(acc[q], s_w[q]);
+            zsum[q] = f4_mul(acc[q], zs[zswz<Q>(tid, q)]);
         }
     }
-    // lanes with the same column: xor-reduce over the lane bits above log2(Q)
+    if (NPT > 1 && tid < n_hi) {               // (this thread's own rows: no barrier needed)
+        const int n = tid + PP_THREADS;
 #pragma unroll
-    for (int o = Q; o < 32; o <<= 1) {
-        zsum.x += __shfl_xor_sync(FULL, zsum.x, o);
-        zsum.y += __shfl_xor_sync(FULL, zsum.y, o);
-        zsum.z += __shfl_xor_sync(FULL, zsum.z, o);
-        zsum.w += __shfl_xor_sync(FULL, zsum.w, o);
+        for (int q = 0; q < Q; ++q) {
+            const float4 a = acc2[tid * Q + q];
+            wout[n * Q + q] = f4_mul(a, s_w[q]);
+            zsum[q] = f4_add(zsum[q], f4_mul(a, zs[zswz<Q>(n, q)]));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            zsum[q].x += __shfl_xor_sync(FULL, zsum[q].x, o);
+            zsum[q].y += __shfl_xor_sync(FULL, zsum[q].y, o);
+            zsum[q].z += __shfl_xor_sync(FULL, zsum[q].z, o);
+            zsum[q].w += __shfl_xor_sync(FULL, zsum[q].w, o);
+        }
     }
     loss = warp_sum(loss);
-    if (lane < Q) s_zacc[wid][lane] = zsum;
-    if (lane == 0) s_loss[wid] = loss;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s_zacc[wid][q] = zsum[q];
+        s_loss[wid] = loss;
+    }
     __syncthreads();
     if (tid < Q) {
         float4 t = s_zacc[0][tid];
@@ -321,10 +360,11 @@ __global__ void k_unpack_pairs(const uint32_t* __restrict__ packed, int64_t n, i
 }
 
 static size_t pair_smem_bytes(int64_t n_nodes, int dim) {
-    size_t b = size_t(n_nodes) * dim * 4;             // zs
+    const int64_t n_hi = n_nodes > PP_THREADS ? n_nodes - PP_THREADS : 0;
+    size_t b = size_t(n_nodes + n_hi) * dim * 4;       // zs, acc2
     b += size_t(PP_T) * 4 * 2 + size_t(PP_E) * 4;      // pk, gb, lists
-    b += size_t(n_nodes + 1) * 4;                      // lstart
-    b += ((size_t(PP_WARPS) * n_nodes + 1) & ~size_t(1)) * 2;   // wh
+    b += size_t((n_nodes + 1 + 3) & ~int64_t(3)) * 4;  // lstart
+    b += (size_t(PP_WARPS) * n_nodes * 2 + 15) & ~size_t(15);   // wh
     return (b + 15) & ~size_t(15);
 }
 
@@ -332,37 +372,33 @@ constexpr int PAIR_DZ_GROUPS = 24;
 
 static bool pair_shape_ok(int64_t n_nodes, int dim) {
     if (!(dim == 4 || dim == 8 || dim == 16 || dim == 32)) return false;
-    if (n_nodes < 1 || n_nodes > 65534) return false;
-    if (n_nodes * (dim / 4) > int64_t(PP_THREADS) * 8) return false;            // owned cells per thread <= 8
-    return 2 * (pair_smem_bytes(n_nodes, dim) + 1024) <= size_t(max_smem_optin()) + 0 ||
-           pair_smem_bytes(n_nodes, dim) + 1024 <= size_t(max_smem_optin());
+    if (n_nodes < 1 || n_nodes > 2 * PP_THREADS) return false;                  // <= 2 accumulator rows per thread
+    return pair_smem_bytes(n_nodes, dim) + 4096 <= size_t(max_smem_optin());   // + static shared memory, 1 CTA per SM
 }
 
-template <int DIM, int MODE, int OWN>
+template <int DIM, int MODE, int NPT, int KB>
 static int pair_pass_launch(const uint32_t* pairs, const int4* items, int n_items, int n_nodes, const float* z,
                             const float* w, float pair_weight, float* wacc, float* zacc, float* loss_part,
                             cudaStream_t s) {
-    auto kern = k_pair_pass<DIM, MODE, OWN>;
+    auto kern = k_pair_pass<DIM, MODE, NPT, KB>;
     const size_t smem = pair_smem_bytes(n_nodes, DIM);
     if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
-    int kb = 1;
-    while ((1 << kb) < n_nodes) ++kb;
-    kern<<<n_items, PP_THREADS, smem, s>>>(pairs, items, n_nodes, kb, (const float4*)z, (const float4*)w, pair_weight,
+    kern<<<n_items, PP_THREADS, smem, s>>>(pairs, items, n_nodes, (const float4*)z, (const float4*)w, pair_weight,
                                            (float4*)wacc, (float4*)zacc, loss_part);
     TIPB_CHECK_LAUNCH("pair_pass");
     return TIPB_OK;
 }
 
 template <int DIM, int MODE>
-static int pair_pass_own(int own, const uint32_t* pairs, const int4* items, int n_items, int n_nodes, const float* z,
-                         const float* w, float pair_weight, float* wacc, float* zacc, float* loss_part, cudaStream_t s) {
-#define PP_GO(O) return pair_pass_launch<DIM, MODE, O>(pairs, items, n_items, n_nodes, z, w, pair_weight, wacc, zacc, loss_part, s)
-    if (own <= 1) PP_GO(1);
-    if (own <= 2) PP_GO(2);
-    if (own <= 4) PP_GO(4);
-    if (own <= 6) PP_GO(6);
-    PP_GO(8);
+static int pair_pass_pick(const uint32_t* pairs, const int4* items, int n_items, int n_nodes, const float* z,
+                          const float* w, float pair_weight, float* wacc, float* zacc, float* loss_part, cudaStream_t s) {
+#define PP_GO(N, K) return pair_pass_launch<DIM, MODE, N, K>(pairs, items, n_items, n_nodes, z, w, pair_weight, wacc, zacc, loss_part, s)
+    if (n_nodes <= 128) PP_GO(1, 7);
+    if (n_nodes <= PP_THREADS) PP_GO(1, 9);
+    if (n_nodes <= 1024) PP_GO(2, 10);
 #undef PP_GO
+    set_last_error("pair_pass: n_nodes=%d not supported", n_nodes);
+    return TIPB_ERR_UNSUPPORTED;
 }
 
 }  // namespace tipb
@@ -410,14 +446,13 @@ int tipb_pair_bce_pass(const uint32_t* pairs, const int32_t* items, int64_t n_it
     float* wacc = static_cast<float*>(ws);
     float* zacc = wacc + size_t(n_slots_total) * cells;
     float* loss_part = zacc + size_t(n_slots_total) * dim;
-    const int own = int(ceil_div(n_nodes * (dim / 4), PP_THREADS));
     cudaStream_t s = (cudaStream_t)stream;
     const int4* it = reinterpret_cast<const int4*>(items);
 #define PP_DIM(D)                                                                                                   \
-    return sign > 0 ? pair_pass_own<D, 0>(own, pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, \
-                                          zacc, loss_part, s)                                                       \
-                    : pair_pass_own<D, 1>(own, pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, \
-                                          zacc, loss_part, s)
+    return sign > 0 ? pair_pass_pick<D, 0>(pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, zacc, \
+                                           loss_part, s)                                                             \
+                    : pair_pass_pick<D, 1>(pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, zacc, \
+                                           loss_part, s)
     switch (dim) {
         case 4: PP_DIM(4);
         case 8: PP_DIM(8);

@@ -47,7 +47,11 @@ int ensure_dyn_smem(const void* func, size_t bytes) {
     std::lock_guard<std::mutex> lock(mu);
     size_t& cur = granted[std::make_pair(dev, func)];
     if (cur >= bytes) return TIPB_OK;
-    size_t want = size_t(max_smem_optin());
+    // the opt-in limit covers static + dynamic shared memory of the kernel
+    cudaFuncAttributes fa;
+    TIPB_CHECK_CUDA(cudaFuncGetAttributes(&fa, func));
+    const size_t optin = size_t(max_smem_optin());
+    size_t want = optin > fa.sharedSizeBytes ? optin - fa.sharedSizeBytes : 0;
     if (bytes > want) {
         set_last_error("kernel needs %zu bytes of shared memory, device allows %zu", bytes, want);
         return TIPB_ERR_UNSUPPORTED;
