@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--mod", default="cat", choices=["cat", "add"])
     ap.add_argument("--shape", default="polypharmacy", choices=["polypharmacy", "small"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    ap.add_argument("--cpu-sample-relations", type=int, default=48)
+    ap.add_argument("--cpu-sample-relations", type=int, default=160,
+                    help="relations of the workload the CPU reference arm runs per step (its autograd backward costs "
+                         "O(R*E*F): the full 861-relation step takes minutes, see profiles/*cpu_full_step*.json)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -52,6 +54,30 @@ def make_data(shape, mod="cat"):
                                    pd_edges=2_000, seed=1111), "synthetic small (debug) shape"
     return synth.make_tip_data(**synth.POLYPHARMACY, seed=1112), \
         "TIP-%s train step, synthetic polypharmacy shape: 645 drugs, 19081 proteins, 861 relations" % mod
+
+
+def workload_config(workload, mod, data, n_gpus):
+    """the `config` object: names the workload only, identical in both arms (b200 / reference)"""
+    return {"workload": workload, "mod": mod, "directed_dd_edges": int(data["dd_train_idx"].shape[1]),
+            "relations": int(data["n_dd_et"]), "drugs": int(data["n_drug"]), "proteins": int(data["n_prot"]),
+            "parallelism": "relations sharded over %d GPU(s), P-P/P-D replicated" % n_gpus,
+            "neg_sampler": "MT19937 bit-exact (numpy-compatible)",
+            "l2": "per-step working set (index arrays + sampler stream, >0.6 GB) exceeds the 126 MB L2; no flush"}
+
+
+def full_config_cpu_reference():
+    """the one-off same-config measurement of the CPU reference arm (ONE full 861-relation step; tools/cpu_full_step.py),
+    committed under profiles/ -- bounds the ratio taken on the sub-sampled arm"""
+    best = None
+    for name in ("r02a_cpu_full_step_box.json", "r02_cpu_full_step.json"):
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", name)))
+            best = {"file": "profiles/" + name, "seconds_per_step": rec["seconds"], "value": rec["typed_edge_msgs_per_s"],
+                    "cores": rec["cores"], "relations": rec["relations"], "directed_dd_edges": rec["directed_dd_edges"]}
+            break
+        except Exception:
+            continue
+    return best
 
 
 def settings_for(mod):
@@ -165,8 +191,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "mod": args.mod, "sample": res["sample"]},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": workload_config(workload, args.mod, data, args.gpus),
+            "cpu_baseline": dict({k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                                 full_config=full_config_cpu_reference()),
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -188,35 +215,90 @@ def count_library_launches(step_fn):
     return mine, total
 
 
-def measure_dominant_kernel(model, iters):
-    """CUDA-event timing of the layer-1 edge pass (k_seg_aggregate, F_in = 64) launched alone on the
-    current stream, L2 flushed between launches."""
-    from tip_b200 import _lib, ops
-    d = model.data
-    dev = model.device
-    n, r = d.n_drug, d.n_dd_et
-    plan = ops.cached_plan(d.dd_train_idx, n, r, range_list=d.dd_train_range, by_src=False)
-    f_in = model.encoder.rgcn1.in_channels
-    x = torch.randn(n, f_in, device=dev)
-    out = torch.empty(plan.seg_cap * f_in, dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    L = _lib.lib()
-    times = []
-    for i in range(iters + 3):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(L.tipb_seg_aggregate(plan.buf.data_ptr(), plan.n_entries, n, r, x.data_ptr(), n, f_in, out.data_ptr(),
-                                        _lib.stream()), "seg_aggregate")
-        e1.record()
-        e1.synchronize()
-        if i >= 3:
-            times.append(e0.elapsed_time(e1) * 1e-3)
-    S = int(plan.field("counts")[0])
-    e = plan.n_entries
-    alg_bytes = e * (4 + 4 * f_in) + S * 4 * f_in + 4 * (S + 1)      # index + gathered row per edge, H row per segment
-    compulsory = 4 * e + 4 * (S + 1) + 4 * n * f_in + 4 * S * f_in  # each distinct byte once
-    return statistics.mean(times), alg_bytes, compulsory, S
+def profile_serial_steps(model, step_fn, n_steps=3):
+    """Per-kernel device time of a training step with EVERY kernel on one stream (no side streams, no prefetch), so no
+    two kernels overlap and a kernel's duration is its own: CUPTI (torch.profiler) over `n_steps` eager steps after one
+    untimed step in that mode.  -> list of steps, each a list of (kernel name, duration us) in launch order."""
+    from torch.profiler import ProfilerActivity, profile
+    from tip_b200 import layers, neg_sampling as ns
+    layers.SERIAL_STREAMS = True
+    ns.set_prefetch(False)
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+        steps = []
+        for _ in range(n_steps):
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step_fn()
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                   and not e.name.startswith("Memcpy") and not e.name.startswith("Memset")]
+            evs.sort(key=lambda e: e.time_range.start)
+            steps.append([(e.name, float(e.time_range.end - e.time_range.start)) for e in evs])
+    finally:
+        layers.SERIAL_STREAMS = False
+        ns.set_prefetch(True)
+    return steps
+
+
+def roofline_block(model, serial_steps, step_s, peaks):
+    """`roofline` of the bench line: the kernel with the largest share of the (serialised) step, its (A)/t against the
+    measured HBM peak next to its ncu DRAM traffic, the same per kernel family, and the step-level figure"""
+    from tools import roofline as rf
+    W = rf.workload_dims(model)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    per_kernel, per_family = {}, {}
+    for kernels in serial_steps:
+        sm = rf.StepModel(W)
+        for name, us in kernels:
+            fam, alg, formula = sm.label(name)
+            short = rf.short_name(name) if "tipb" in name else "(torch) " + rf.short_name(name)[:48]
+            k = per_kernel.setdefault(short, {"us": 0.0, "launches": 0, "alg": 0, "formula": formula, "family": fam})
+            k["us"] += us
+            k["launches"] += 1
+            k["alg"] += alg or 0
+            f = per_family.setdefault(fam, {"us": 0.0, "alg": 0})
+            f["us"] += us
+            f["alg"] += alg or 0
+    n = float(len(serial_steps))
+    total_us = sum(k["us"] for k in per_kernel.values()) / n
+    mine = {k: v for k, v in per_kernel.items() if not k.startswith("(torch)")}
+    dom = max(mine, key=lambda k: mine[k]["us"])
+    dk = mine[dom]
+    launches = dk["launches"] / n
+    k_us = dk["us"] / dk["launches"]                       # average launch duration
+    alg = dk["alg"] / dk["launches"] if dk["alg"] else None
+    traffic, traffic_src = None, None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        if dom in t["kernels"]:
+            traffic, traffic_src = t["kernels"][dom]["traffic_bytes"], t["source"]
+    except Exception:
+        pass
+    achieved = alg / (k_us * 1e-6) / 1e9 if alg else None
+    fam_rows = []
+    for fam, v in sorted(per_family.items(), key=lambda kv: -kv[1]["us"]):
+        us = v["us"] / n
+        a = v["alg"] / n
+        fam_rows.append({"family": fam, "us": round(us, 1), "share": round(us / total_us, 4),
+                         "algorithmic_bytes": int(a) if a else None,
+                         "frac": round(a / (us * 1e-6) / 1e9 / peak, 3) if a else None})
+    step_alg = rf.step_algorithmic_bytes(W)
+    block = {"bound": "hbm", "kernel": dom, "kernel_family": dk["family"], "kernel_share_of_step": round(dk["us"] / n / total_us, 4),
+             "kernel_us": round(k_us, 2), "kernel_launches_per_step": launches,
+             "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6.65 TB/s",
+             "unit": "GB/s", "frac": achieved / peak if achieved else None, "algorithmic_bytes": int(alg) if alg else None,
+             "formula": dk["formula"], "traffic": traffic, "traffic_source": traffic_src,
+             "dram_frac": traffic / (k_us * 1e-6) / 1e9 / peak if traffic else None,
+             "how": "kernel durations: CUPTI over %d eager steps with every kernel on ONE stream (no overlap); the kernel "
+                    "is the library kernel with the largest summed time in that step" % len(serial_steps),
+             "serial_step_us": round(total_us, 1),
+             "step": {"algorithmic_bytes": int(step_alg), "frac_of_timed_step": step_alg / step_s / 1e9 / peak,
+                      "what": "SURVEY 8(d): sum of (A) over the step / the timed (overlapped, CUDA-graph) step time"},
+             "families": fam_rows,
+             "note": "(A) counts gathered payload rows, which this path serves from shared memory; where frac > 1 the "
+                     "kernel is not HBM-bound (issue / shared-memory bound) and dram_frac is the DRAM-pin figure"}
+    return block
 
 
 def run_b200_arm(args):
@@ -325,41 +407,24 @@ def run_b200_arm(args):
         e2e = None
     launches, launches_all = count_library_launches(step)   # every rank runs it: the step contains collectives
 
+    serial = profile_serial_steps(model, step, 3)            # every rank runs it: the step contains collectives
     if rank == 0:
-        k_time, alg_bytes, compulsory, n_seg = measure_dominant_kernel(model, max(args.steps, 10))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / k_time / 1e9
-        traffic, traffic_src = None, None
-        try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the committed ncu --set full capture
-            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")))
-            traffic, traffic_src = t["traffic_bytes"], t["source"]
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": "k_seg_aggregate_flat<F=64> (R-GCN layer-1 edge pass)", "achieved": achieved,
-                    "peak": peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                    "kernel_us": k_time * 1e6,
-                    "algorithmic_bytes": alg_bytes, "compulsory_dram_bytes": compulsory,
-                    "compulsory_frac": compulsory / k_time / 1e9 / peak, "segments": n_seg,
-                    "note": "features are staged in shared memory: achieved counts gathered bytes (SURVEY 8d figure A), "
-                            "compulsory_frac counts each distinct DRAM byte once (figure B)"}
+        roofline = roofline_block(model, serial, step_s, peaks)
         cpu = None
         if not args.skip_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             cpu = time_cpu_reference(data, args.mod, args.cpu_sample_relations, 1, 1)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = dict({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                       full_config=full_config_cpu_reference())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "mod": args.mod, "directed_dd_edges": e_total,
-                           "parallelism": "relations sharded over %d GPU(s), P-P/P-D replicated" % world,
-                           "cuda_graph": graph is not None, "neg_sampler": "MT19937 bit-exact (numpy-compatible)",
-                           "l2": "per-step working set (index arrays + sampler stream, >0.6 GB) exceeds the 126 MB L2; no flush"},
+                "config": workload_config(workload, args.mod, data, world), "cuda_graph": graph is not None,
                 "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                 "all_cuda_kernels_per_step": launches_all, "loss": loss_value}

@@ -223,11 +223,12 @@ int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* stream_words
  * Usable when z (n_nodes x dim fp32) fits in shared memory: tipb_pair_pass_supported; otherwise use the
  * tipb_decoder_bce_fused path above.
  *   pairs    packed (row << 16 | col), all pairs of relation r contiguous
- *   items    int32 [n_items,4] = (relation, first pair, pair count <= tipb_pair_chunk(), slot), built by the caller from
- *            the relation ranges (static per graph), largest first; a slot receives one item's partial results
+ *   items    int32 [n_items,4] = (relation, first pair, pair count <= tipb_pair_chunk(), slot | pass << 30), the work items
+ *            of BOTH passes (pass 0: positive pairs, 1: negative pairs) in one launch, built by the caller from the
+ *            relation ranges (static per graph), largest first; a slot receives one item's partial results
  *   slots    the positive pass's slots come first, each pass numbers its slots relation-major;
  *            rel_slot_ptr = int32 [2 * (n_rel + 1)]: slot ranges per relation of the positive, then the negative pass
- *   pair_weight  multiplicity / number of scored entries: 2/E for the first halves of a mirrored edge set
+ *   pos_weight / neg_weight  multiplicity / number of scored entries: 2/E for the first halves of a mirrored edge set
  *            (src/utils.py:17-23: every undirected pair stands for two directed entries), 1/E for negatives */
 int tipb_pair_pass_supported(int64_t n_nodes, int dim);
 int64_t tipb_pair_chunk(void);
@@ -235,9 +236,9 @@ size_t tipb_pair_workspace_bytes(int64_t n_slots_total, int64_t n_nodes, int dim
 int tipb_pack_half_pairs(const int64_t* edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_rel,
                          int64_t n_nodes, uint32_t* packed /* [n_edges / 2] */, int32_t* status, void* stream);
 int tipb_unpack_pairs(const uint32_t* packed, int64_t n, int64_t* edge_index /* [2,n] */, void* stream);
-int tipb_pair_bce_pass(const uint32_t* pairs, const int32_t* items, int64_t n_items, int64_t n_slots_total,
-                       int64_t n_nodes, const float* z, const float* weight, int dim, int sign, float pair_weight,
-                       void* ws, size_t ws_bytes, void* stream);
+int tipb_pair_bce_pass(const uint32_t* pos_pairs, const uint32_t* neg_pairs, const int32_t* items, int64_t n_items,
+                       int64_t n_slots_total, int64_t n_nodes, const float* z, const float* weight, int dim,
+                       float pos_weight, float neg_weight, void* ws, size_t ws_bytes, void* stream);
 int tipb_pair_bce_finish(const int32_t* rel_slot_ptr, int64_t n_slots_total, int64_t n_nodes, int64_t n_rel, int dim,
                          float* loss_out /* [1] */, float* d_z, float* d_weight, void* ws, size_t ws_bytes,
                          void* stream);

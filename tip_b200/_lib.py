@@ -53,7 +53,7 @@ SIGNATURES = {
     "tipb_pair_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "tipb_pack_half_pairs": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "tipb_unpack_pairs": (C.c_int, [_p, _i64, _p, _p]),
-    "tipb_pair_bce_pass": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i32, C.c_float, _p, _sz, _p]),
+    "tipb_pair_bce_pass": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _i32, C.c_float, C.c_float, _p, _sz, _p]),
     "tipb_pair_bce_finish": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "tipb_eval_workspace_bytes": (_sz, [_i64, _i64]),
     "tipb_eval_auprc_auroc_ap": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),

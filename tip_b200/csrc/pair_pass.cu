@@ -51,11 +51,14 @@ __device__ __forceinline__ unsigned same_key_lanes(int key, bool valid) {
     return peers;
 }
 
-template <int DIM, int MODE, int NPT, int KB>
+constexpr int PP_NEG_FLAG = 1 << 30;      // items[].w = slot | PP_NEG_FLAG for a work item of the negative pass
+
+template <int DIM, int NPT, int KB>
 __global__ void __launch_bounds__(PP_THREADS, DIM >= 32 ? 1 : 2)
-k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, int n_nodes,
-            const float4* __restrict__ z, const float4* __restrict__ w, float pair_weight,
-            float4* __restrict__ wacc, float4* __restrict__ zacc, float* __restrict__ loss_part) {
+k_pair_pass(const uint32_t* __restrict__ pos_pairs, const uint32_t* __restrict__ neg_pairs,
+            const int4* __restrict__ items, int n_nodes, const float4* __restrict__ z, const float4* __restrict__ w,
+            float pos_weight, float neg_weight, float4* __restrict__ wacc, float4* __restrict__ zacc,
+            float* __restrict__ loss_part) {
     constexpr int Q = DIM / 4;
     extern __shared__ float4 pp_smem[];
     float4* zs = pp_smem;                                              // [n_nodes * Q], swizzled
@@ -73,8 +76,11 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int4 item = items[blockIdx.x];       // rel, first pair, pair count, slot
-    const int rel = item.x, p0 = item.y, np = item.z, slot = item.w;
+    const int4 item = items[blockIdx.x];       // rel, first pair, pair count, slot | pass flag
+    const int rel = item.x, p0 = item.y, np = item.z, slot = item.w & (PP_NEG_FLAG - 1);
+    const bool negative = (item.w & PP_NEG_FLAG) != 0;          // uniform over the CTA
+    const uint32_t* __restrict__ pairs = (negative ? neg_pairs : pos_pairs) + size_t(p0);
+    const float pair_weight = negative ? neg_weight : pos_weight;
 
     for (int i = tid; i < n_nodes * Q; i += PP_THREADS) zs[zswz<Q>(i / Q, i % Q)] = z[i];
     for (int i = tid; i < n_hi * Q; i += PP_THREADS) acc2[i] = f4_zero();
@@ -89,10 +95,23 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
     const int per = (n_nodes + PP_THREADS - 1) / PP_THREADS;   // nodes per thread in the scan
     const int wh_vec = (PP_WARPS * n_nodes * 2 + 15) / 16;     // uint4 words of wh
 
+    // the next tile's pairs are fetched into registers while the current tile is processed
+    uint32_t nxt[PP_T / PP_THREADS];
+#pragma unroll
+    for (int u = 0; u < PP_T / PP_THREADS; ++u) {
+        const int t = tid + u * PP_THREADS;
+        nxt[u] = t < np ? ld_stream_i32(reinterpret_cast<const int*>(pairs) + t) : 0u;
+    }
     for (int t0 = 0; t0 < np; t0 += PP_T) {
         const int nt = min(PP_T, np - t0);
         __syncthreads();                       // previous tile fully consumed (and zs staged, first trip)
-        for (int t = tid; t < nt; t += PP_THREADS) pk[t] = pairs[size_t(p0) + t0 + t];
+#pragma unroll
+        for (int u = 0; u < PP_T / PP_THREADS; ++u) {
+            const int t = tid + u * PP_THREADS;
+            pk[t] = nxt[u];
+            const int tn = t0 + PP_T + t;
+            nxt[u] = tn < np ? ld_stream_i32(reinterpret_cast<const int*>(pairs) + tn) : 0u;
+        }
         for (int i = tid; i < wh_vec; i += PP_THREADS) reinterpret_cast<uint4*>(wh)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
 
@@ -104,16 +123,12 @@ k_pair_pass(const uint32_t* __restrict__ pairs, const int4* __restrict__ items, 
 #pragma unroll
             for (int q = 0; q < Q; ++q) v += f4_dot(f4_mul(zs[zswz<Q>(i, q)], s_w[q]), zs[zswz<Q>(j, q)]);
             const float sg = __frcp_rn(1.0f + __expf(-v));
-            float g;
-            if (MODE == 0) {                   // positives: -log(s + eps)
-                loss -= __logf(sg + PAIR_EPS);
-                g = -__fdividef(sg * (1.f - sg), sg + PAIR_EPS);
-            } else {                           // negatives: -log(1 - s + eps)
-                const float om = 1.f - sg;
-                loss -= __logf(om + PAIR_EPS);
-                g = __fdividef(sg * om, om + PAIR_EPS);
-            }
-            gb[t] = g * pair_weight;
+            // positives: -log(s + eps), d/dv = -s (1 - s) / (s + eps);  negatives: -log(1 - s + eps), d/dv = s (1 - s) / (1 - s + eps)
+            const float om = 1.f - sg;
+            const float arg = (negative ? om : sg) + PAIR_EPS;
+            loss -= __logf(arg);
+            const float g = __fdividef(sg * om, arg);
+            gb[t] = negative ? g * pair_weight : -g * pair_weight;
         }
 
         // ---- group the 2 nt pair-ends by node: count (stable rank inside the warp's run) ...
@@ -376,23 +391,24 @@ static bool pair_shape_ok(int64_t n_nodes, int dim) {
     return pair_smem_bytes(n_nodes, dim) + 4096 <= size_t(max_smem_optin());   // + static shared memory, 1 CTA per SM
 }
 
-template <int DIM, int MODE, int NPT, int KB>
-static int pair_pass_launch(const uint32_t* pairs, const int4* items, int n_items, int n_nodes, const float* z,
-                            const float* w, float pair_weight, float* wacc, float* zacc, float* loss_part,
-                            cudaStream_t s) {
-    auto kern = k_pair_pass<DIM, MODE, NPT, KB>;
+template <int DIM, int NPT, int KB>
+static int pair_pass_launch(const uint32_t* pos_pairs, const uint32_t* neg_pairs, const int4* items, int n_items,
+                            int n_nodes, const float* z, const float* w, float pos_weight, float neg_weight, float* wacc,
+                            float* zacc, float* loss_part, cudaStream_t s) {
+    auto kern = k_pair_pass<DIM, NPT, KB>;
     const size_t smem = pair_smem_bytes(n_nodes, DIM);
     if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
-    kern<<<n_items, PP_THREADS, smem, s>>>(pairs, items, n_nodes, (const float4*)z, (const float4*)w, pair_weight,
-                                           (float4*)wacc, (float4*)zacc, loss_part);
+    kern<<<n_items, PP_THREADS, smem, s>>>(pos_pairs, neg_pairs, items, n_nodes, (const float4*)z, (const float4*)w,
+                                           pos_weight, neg_weight, (float4*)wacc, (float4*)zacc, loss_part);
     TIPB_CHECK_LAUNCH("pair_pass");
     return TIPB_OK;
 }
 
-template <int DIM, int MODE>
-static int pair_pass_pick(const uint32_t* pairs, const int4* items, int n_items, int n_nodes, const float* z,
-                          const float* w, float pair_weight, float* wacc, float* zacc, float* loss_part, cudaStream_t s) {
-#define PP_GO(N, K) return pair_pass_launch<DIM, MODE, N, K>(pairs, items, n_items, n_nodes, z, w, pair_weight, wacc, zacc, loss_part, s)
+template <int DIM>
+static int pair_pass_pick(const uint32_t* pos_pairs, const uint32_t* neg_pairs, const int4* items, int n_items,
+                          int n_nodes, const float* z, const float* w, float pos_weight, float neg_weight, float* wacc,
+                          float* zacc, float* loss_part, cudaStream_t s) {
+#define PP_GO(N, K) return pair_pass_launch<DIM, N, K>(pos_pairs, neg_pairs, items, n_items, n_nodes, z, w, pos_weight, neg_weight, wacc, zacc, loss_part, s)
     if (n_nodes <= 128) PP_GO(1, 7);
     if (n_nodes <= PP_THREADS) PP_GO(1, 9);
     if (n_nodes <= 1024) PP_GO(2, 10);
@@ -433,13 +449,13 @@ int tipb_unpack_pairs(const uint32_t* packed, int64_t n, int64_t* edge_index, vo
     return TIPB_OK;
 }
 
-// one pass (sign +1: positives, -1: negatives) over `n_items` work items; results go to slots [slot_base, ...) of ws
-int tipb_pair_bce_pass(const uint32_t* pairs, const int32_t* items, int64_t n_items, int64_t n_slots_total,
-                       int64_t n_nodes, const float* z, const float* weight, int dim, int sign, float pair_weight,
-                       void* ws, size_t ws_bytes, void* stream) {
-    TIPB_CHECK_ARG(pairs && items && z && weight && ws, "pair_bce_pass: NULL argument");
-    TIPB_CHECK_ARG(sign == 1 || sign == -1, "pair_bce_pass: sign must be +1 (positives) or -1 (negatives)");
+// both passes in one launch: work items of the positive pairs and of the negative pairs (flagged in items[].w)
+int tipb_pair_bce_pass(const uint32_t* pos_pairs, const uint32_t* neg_pairs, const int32_t* items, int64_t n_items,
+                       int64_t n_slots_total, int64_t n_nodes, const float* z, const float* weight, int dim,
+                       float pos_weight, float neg_weight, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(pos_pairs && neg_pairs && items && z && weight && ws, "pair_bce_pass: NULL argument");
     TIPB_CHECK_ARG(pair_shape_ok(n_nodes, dim), "pair_bce_pass: shape not supported (use the typed-CSR decoder path)");
+    TIPB_CHECK_ARG(n_slots_total < PP_NEG_FLAG, "pair_bce_pass: too many slots");
     TIPB_CHECK_ARG(ws_bytes >= tipb_pair_workspace_bytes(n_slots_total, n_nodes, dim), "pair_bce_pass: workspace too small");
     if (n_items == 0) return TIPB_OK;
     const size_t cells = size_t(n_nodes) * dim;
@@ -449,10 +465,8 @@ int tipb_pair_bce_pass(const uint32_t* pairs, const int32_t* items, int64_t n_it
     cudaStream_t s = (cudaStream_t)stream;
     const int4* it = reinterpret_cast<const int4*>(items);
 #define PP_DIM(D)                                                                                                   \
-    return sign > 0 ? pair_pass_pick<D, 0>(pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, zacc, \
-                                           loss_part, s)                                                             \
-                    : pair_pass_pick<D, 1>(pairs, it, (int)n_items, (int)n_nodes, z, weight, pair_weight, wacc, zacc, \
-                                           loss_part, s)
+    return pair_pass_pick<D>(pos_pairs, neg_pairs, it, (int)n_items, (int)n_nodes, z, weight, pos_weight, neg_weight, \
+                             wacc, zacc, loss_part, s)
     switch (dim) {
         case 4: PP_DIM(4);
         case 8: PP_DIM(8);

@@ -402,7 +402,9 @@ class TIP(nn.Module):
         cur = torch.cuda.current_stream(self.device)
         side = cur if SERIAL_STREAMS else self._side
         # ---- fused pair pass (csrc/pair_pass.cu): mirrored edge set + z fits in shared memory (the polypharmacy shape)
-        plan = ops.pair_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, d.dd_train_range, self.settings.n_hid2)
+        member = _ns._membership(d.dd_train_idx, d.n_drug, d.dd_train_range)     # cached; holds a host copy of the ranges
+        plan = ops.pair_plan(d.dd_train_idx, d.n_drug, d.n_dd_et, d.dd_train_range, self.settings.n_hid2,
+                             rl_host=member.rl_host, validate=check_status)
         if plan is not None:
             if self._neg_packed is None or self._neg_packed.numel() != d.dd_train_idx.shape[1]:
                 self._neg_packed = torch.empty(d.dd_train_idx.shape[1], dtype=torch.int32, device=self.device)

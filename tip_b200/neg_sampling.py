@@ -154,6 +154,7 @@ class _Membership(object):
         self.num_nodes = int(num_nodes)
         self.range_dev = _i64c(range_list.to(device=dev, dtype=torch.long))
         rl = np.ascontiguousarray(self.range_dev.cpu().numpy())        # one-time host copy (setup, not per step)
+        self.rl_host = rl
         sizes = rl[:, 1] - rl[:, 0]
         if self.n_rel and not (np.all(sizes >= 0) and np.all(rl[1:, 0] == rl[:-1, 1]) and rl[0, 0] == 0
                                and rl[-1, 1] == self.n_edges):

@@ -120,6 +120,7 @@ def clear_plan_cache():
     _plan_cache.clear()
     _dec_plans.clear()
     _pair_plans.clear()
+    _item_tables.clear()
     _mirror_cache.clear()
 
 
@@ -449,60 +450,76 @@ def _pair_items(ranges, chunk, slot_base):
     """work items (relation, first pair, pair count, slot) of one pass: every relation's pairs [start, end) cut into
     near-equal chunks of at most `chunk` pairs; slots numbered relation-major from `slot_base`; rows ordered largest
     first (the launch order).  -> (items int32 [n,4], rel_slot_ptr int32 [n_rel+1] absolute, n_slots)"""
-    rows, ptr_ = [], [slot_base]
-    slot = slot_base
-    for r, (a, b) in enumerate(ranges):
-        a, b = int(a), int(b)
-        n = b - a
-        if n > 0:
-            k = -(-n // chunk)
-            base, extra = divmod(n, k)
-            start = a
-            for c in range(k):
-                cnt = base + (1 if c < extra else 0)
-                rows.append((r, start, cnt, slot))
-                start += cnt
-                slot += 1
-        ptr_.append(slot)
-    items = np.asarray(rows, dtype=np.int32).reshape(-1, 4)
-    order = np.argsort(-items[:, 2], kind="stable") if len(rows) else np.zeros(0, dtype=np.int64)
-    return np.ascontiguousarray(items[order]), np.asarray(ptr_, dtype=np.int32), slot - slot_base
+    ranges = np.asarray(ranges, dtype=np.int64).reshape(-1, 2)
+    n = ranges[:, 1] - ranges[:, 0]
+    k = -(-n // chunk)                                    # chunks per relation (0 for an empty relation)
+    ptr_ = np.concatenate([[0], np.cumsum(k)]) + slot_base
+    total = int(k.sum())
+    rel = np.repeat(np.arange(ranges.shape[0]), k)
+    c = np.arange(total) - np.repeat(ptr_[:-1] - slot_base, k)      # chunk index inside its relation
+    base, extra = n[rel] // np.maximum(k[rel], 1), n[rel] % np.maximum(k[rel], 1)
+    cnt = base + (c < extra)
+    start = ranges[rel, 0] + c * base + np.minimum(c, extra)
+    items = np.stack([rel, start, cnt, np.arange(total) + slot_base], axis=1).astype(np.int32).reshape(-1, 4)
+    order = np.argsort(-items[:, 2], kind="stable")
+    return np.ascontiguousarray(items[order]), ptr_.astype(np.int32), total
+
+
+_item_tables = {}      # (range bytes, chunk) -> host/device item tables: they depend on the relation sizes only
 
 
 class PairPlan(object):
     """Static tables of the fused pair pass (csrc/pair_pass.cu) for one mirrored, relation-sorted edge set: the
     positive pairs (first half of every relation range, packed), the work items of the positive and the negative
-    pass, and their relation-major slot ranges.  Built once per graph (one small host copy of range_list)."""
+    pass, and their relation-major slot ranges.  Built once per graph; the item tables depend on the relation sizes
+    only and are shared between graphs with the same ranges (`rl_host`: a host copy of range_list if the caller has
+    one, otherwise one small device->host copy is made)."""
 
-    def __init__(self, edge_index, n_nodes, n_rel, range_list):
+    def __init__(self, edge_index, n_nodes, n_rel, range_list, rl_host=None):
         L = lib()
         dev = edge_index.device
         self.device, self.n_nodes, self.n_rel = dev, int(n_nodes), int(n_rel)
         self.n_edges = int(edge_index.shape[1])
         rl_dev = _i64c(range_list.to(device=dev, dtype=torch.long))
-        rl = rl_dev.cpu().numpy()
-        check_cumulative_ranges(rl, self.n_edges)
+        rl = np.ascontiguousarray(rl_dev.cpu().numpy() if rl_host is None else np.asarray(rl_host, dtype=np.int64))
         chunk = int(L.tipb_pair_chunk())
-        items_pos, ptr_pos, n_pos = _pair_items(rl // 2, chunk, 0)
-        items_neg, ptr_neg, n_neg = _pair_items(rl, chunk, n_pos)
-        self.n_slots = n_pos + n_neg
-        self.n_items_pos, self.n_items_neg = int(items_pos.shape[0]), int(items_neg.shape[0])
-        self.items_pos = torch.from_numpy(items_pos).to(dev)
-        self.items_neg = torch.from_numpy(items_neg).to(dev)
-        self.rel_slot_ptr = torch.from_numpy(np.concatenate([ptr_pos, ptr_neg])).to(dev)
+        key = (rl.tobytes(), chunk, str(dev))
+        tables = _item_tables.get(key)
+        if tables is None:
+            check_cumulative_ranges(rl, self.n_edges)
+            items_pos, ptr_pos, n_pos = _pair_items(rl // 2, chunk, 0)
+            items_neg, ptr_neg, n_neg = _pair_items(rl, chunk, n_pos)
+            items_neg[:, 3] |= 1 << 30                       # pass flag (csrc/pair_pass.cu: PP_NEG_FLAG)
+            items = np.concatenate([items_pos, items_neg])
+            items = np.ascontiguousarray(items[np.argsort(-items[:, 2], kind="stable")])    # one launch, largest first
+            if len(_item_tables) > 8:
+                _item_tables.clear()
+            tables = _item_tables[key] = (n_pos + n_neg, int(items.shape[0]), torch.from_numpy(items).to(dev),
+                                          torch.from_numpy(np.concatenate([ptr_pos, ptr_neg])).to(dev))
+        self.n_slots, self.n_items, self.items, self.rel_slot_ptr = tables
         self.pos_packed = torch.empty(max(self.n_edges // 2, 1), dtype=torch.int32, device=dev)
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            check(L.tipb_pack_half_pairs(ptr(_i64c(edge_index)), ptr(rl_dev), self.n_edges, self.n_rel, self.n_nodes,
-                                         ptr(self.pos_packed), ptr(status), stream()), "pack_half_pairs")
-        if int(status.item()) != 0:
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._rl_dev = rl_dev
+        self.repack(edge_index)
+
+    def repack(self, edge_index):
+        """(re)pack the positive pairs from edge_index (same ranges): device work only, no host synchronisation"""
+        with torch.cuda.device(self.device):
+            check(lib().tipb_pack_half_pairs(ptr(_i64c(edge_index)), ptr(self._rl_dev), self.n_edges, self.n_rel,
+                                             self.n_nodes, ptr(self.pos_packed), ptr(self.status), stream()),
+                  "pack_half_pairs")
+
+    def check_status(self):
+        """One host sync: raises if an edge endpoint was out of range when the pairs were packed."""
+        if int(self.status.item()) != 0:
             raise IndexError("edge_index contains an out-of-range node id")
+        return self
 
 
 _pair_plans = {}
 
 
-def pair_plan(edge_index, n_nodes, n_rel, range_list, dim):
+def pair_plan(edge_index, n_nodes, n_rel, range_list, dim, rl_host=None, validate=True):
     """the PairPlan of a graph, or None when the fused pair pass does not apply: the edge set must be mirrored
     (src/utils.py:17-23) and z (n_nodes x dim, dim padded to a power of two) must fit in shared memory"""
     if not lib().tipb_pair_pass_supported(int(n_nodes), _next_pow2(int(dim))):
@@ -515,7 +532,10 @@ def pair_plan(edge_index, n_nodes, n_rel, range_list, dim):
     if hit is None or hit[0] != versions:
         if len(_pair_plans) > 8:
             _pair_plans.clear()
-        hit = _pair_plans[key] = (versions, PairPlan(edge_index, n_nodes, n_rel, range_list), (edge_index, range_list))
+        plan = PairPlan(edge_index, n_nodes, n_rel, range_list, rl_host=rl_host)
+        if validate:
+            plan.check_status()
+        hit = _pair_plans[key] = (versions, plan, (edge_index, range_list))
     return hit[1]
 
 
@@ -533,12 +553,11 @@ class _PairBCEFunction(torch.autograd.Function):
         d_z, d_w = torch.empty_like(z), torch.empty_like(weight)
         ws = workspace(L.tipb_pair_workspace_bytes(plan.n_slots, n_nodes, dim), z.device, "pair")
         e = float(max(plan.n_edges, 1))
-        check(L.tipb_pair_bce_pass(ptr(plan.pos_packed), ptr(plan.items_pos), plan.n_items_pos, plan.n_slots, n_nodes, ptr(z),
-                                   ptr(weight), dim, 1, 2.0 / e, ptr(ws), ws.numel(), stream()), "pair_bce_pass(pos)")
-        if neg_stream is not None:      # the negatives are sampled on a side stream; the positive pass did not need them
+        if neg_stream is not None:      # the negatives were sampled on a side stream while the encoder ran
             torch.cuda.current_stream(z.device).wait_stream(neg_stream)
-        check(L.tipb_pair_bce_pass(ptr(neg_packed), ptr(plan.items_neg), plan.n_items_neg, plan.n_slots, n_nodes, ptr(z),
-                                   ptr(weight), dim, -1, 1.0 / e, ptr(ws), ws.numel(), stream()), "pair_bce_pass(neg)")
+        check(L.tipb_pair_bce_pass(ptr(plan.pos_packed), ptr(neg_packed), ptr(plan.items), plan.n_items, plan.n_slots,
+                                   n_nodes, ptr(z), ptr(weight), dim, 2.0 / e, 1.0 / e, ptr(ws), ws.numel(), stream()),
+              "pair_bce_pass")
         check(L.tipb_pair_bce_finish(ptr(plan.rel_slot_ptr), plan.n_slots, n_nodes, n_rel, dim, ptr(loss), ptr(d_z), ptr(d_w),
                                      ptr(ws), ws.numel(), stream()), "pair_bce_finish")
         ctx.save_for_backward(d_z, d_w)
