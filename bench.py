@@ -38,7 +38,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mod", default="cat", choices=["cat", "add"])
-    ap.add_argument("--shape", default="polypharmacy", choices=["polypharmacy", "small"])
+    ap.add_argument("--shape", default="polypharmacy", choices=["polypharmacy", "small", "scaled"],
+                    help="scaled = BASELINE.json config 4 (10k drugs, 100k proteins, 4k relations, ~50M directed D-D edges)")
+    ap.add_argument("--model", default="tip", choices=["tip", "dd"],
+                    help="dd = BASELINE.json config 3: the D-D-only R-GCN of test/dd_net_scalable.py, relation-sharded")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--cpu-sample-relations", type=int, default=160,
                     help="relations of the workload the CPU reference arm runs per step (its autograd backward costs "
@@ -52,6 +55,9 @@ def make_data(shape, mod="cat"):
     if shape == "small":
         return synth.make_tip_data(n_drug=200, n_prot=2000, n_rel=40, dd_undirected=60_000, pp_undirected=20_000,
                                    pd_edges=2_000, seed=1111), "synthetic small (debug) shape"
+    if shape == "scaled":
+        return synth.make_tip_data(**synth.SCALED, seed=1114), \
+            "TIP-%s train step, scaled synthetic graph: 10000 drugs, 100000 proteins, 4000 relations" % mod
     return synth.make_tip_data(**synth.POLYPHARMACY, seed=1112), \
         "TIP-%s train step, synthetic polypharmacy shape: 645 drugs, 19081 proteins, 861 relations" % mod
 
@@ -318,11 +324,19 @@ def run_b200_arm(args):
     e_total = int(data["dd_train_idx"].shape[1])
     torch.manual_seed(1111)
     ns.seed(1111, dev)
-    if world > 1:
+    if args.model == "dd":
+        workload = workload.replace("TIP-%s train step" % args.mod, "D-D-only R-GCN (test/dd_net_scalable.py) train step")
+    if world > 1 or args.model == "dd":
         from tip_b200 import parallel
-        model = parallel.ShardedTIP(settings_for(args.mod), dev, mod=args.mod, data=data, rank=rank, world=world)
+        # the sampler's all-gather runs on a side stream: give it its own communicator so that it does not queue
+        # behind the encoder's all-reduces on NCCL's stream
+        coll = parallel._Collective(world, sampler_group=dist.new_group() if world > 1 else None)
+        cls = parallel.ShardedDDNet if args.model == "dd" else parallel.ShardedTIP
+        model = cls(settings_for(args.mod), dev, mod=args.mod, data=data, rank=rank, world=world, collective=coll,
+                    defer_loss_reduce=world > 1)
     else:
         model = layers.TIP(settings_for(args.mod), dev, mod=args.mod, data=data)
+    sharded = hasattr(model, "refresh_shard")
     if os.environ.get("TIPB_BENCH_TORCH_ADAM") == "1":
         opt = torch.optim.Adam(model.parameters(), lr=model.settings.lr, capturable=True, fused=True)
     else:       # tip.py:21 `torch.optim.Adam(model.parameters(), lr)` as one launch of the library (csrc/adam.cu)
@@ -333,11 +347,9 @@ def run_b200_arm(args):
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)
         loss.backward()
-        if world > 1:
-            model.sync_gradients()
         opt.step()
         ns.join_prefetch(dev)        # the next step's MT19937 words were generated on a side stream meanwhile
-        return loss
+        return model.last_loss if getattr(model, "defer_loss_reduce", False) else loss
 
     def barrier():
         if world > 1:
@@ -399,7 +411,7 @@ def run_b200_arm(args):
     if static_loss is not None:
         loss_value = float(static_loss)
     try:
-        e2e = measure_e2e(model, opt, data, args.steps, e_total, world)
+        e2e = measure_e2e(model, opt, data, args.steps, e_total, world, sharded)
     except Exception as exc:      # keep the device-timed line if the end-to-end loop fails (the same way on every rank)
         if world == 1:
             raise
@@ -438,27 +450,34 @@ def run_b200_arm(args):
         os._exit(0)
 
 
-def measure_e2e(model, opt, data, steps, e_total, world=1):
-    """every rank copies the graph tensors from its pinned host memory and rebuilds its index structures; wall clock
-    between barriers, max over ranks"""
+def measure_e2e(model, opt, data, steps, e_total, world=1, sharded=False):
+    """every rank copies ITS inputs of the step from pinned host memory -- the graph tensors the path reads, int64 as the
+    reference API has them (a sharded rank: its relations' edges only; `dd_train_et` is not copied: like the reference's
+    MyRGCNConv2 the path takes relation membership from range_list) -- rebuilds its index structures from them, trains
+    one step and reads the loss back; wall clock between barriers, max over ranks"""
     import torch.distributed as dist
     dev = model.device
-    names = ("dd_train_idx", "dd_train_et", "dd_train_range", "pp_train_indices", "dp_edge_index", "d_norm")
-    host = {k: data[k].contiguous().pin_memory() for k in names}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
     d = model.data
+    pairs = []          # (device tensor, pinned host tensor)
+    if sharded:
+        pairs.append((model.local_idx, data["dd_train_idx"][:, model.e_lo:model.e_hi].contiguous().pin_memory()))
+    else:
+        pairs.append((d.dd_train_idx, data["dd_train_idx"].contiguous().pin_memory()))
+    for k in ("dd_train_range", "pp_train_indices", "dp_edge_index", "d_norm"):
+        pairs.append((getattr(d, k), data[k].to(getattr(d, k).dtype).contiguous().pin_memory()))
+    h2d = sum(h.numel() * h.element_size() for _, h in pairs)
 
     def e2e_step():
-        for k in names:                       # host -> device, in place: the version bump makes every cached typed CSR /
-            getattr(d, k).copy_(host[k], non_blocking=True)   # bitmap rebuild itself (into the same buffers)
-        model.invalidate_graph_caches()
+        for dst, src in pairs:                # host -> device, in place: the version bump makes every cached typed CSR /
+            dst.copy_(src, non_blocking=True)         # bitmap rebuild itself (into the same buffers)
+        if sharded:
+            model.refresh_shard()
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)
         loss.backward()
-        if world > 1:
-            model.sync_gradients()
         opt.step()
-        return loss.item()                    # device -> host
+        out = model.last_loss if getattr(model, "defer_loss_reduce", False) else loss
+        return out.item()                     # device -> host
 
     def fence():
         if world > 1:
@@ -476,11 +495,14 @@ def measure_e2e(model, opt, data, steps, e_total, world=1):
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t)
-    return {"value": 4.0 * e_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+        h = torch.tensor([h2d], device=dev, dtype=torch.float64)
+        dist.all_reduce(h, op=dist.ReduceOp.SUM)
+        dt, h2d = float(t), int(h)
+    return {"value": 4.0 * e_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
             "ms_per_step": dt * 1e3,
-            "what": "per rank: pinned-host graph tensors -> device, all typed CSRs / bitmaps rebuilt, one train step, "
-                    "loss.item(); wall clock between barriers, max over ranks"}
+            "what": "per rank: its graph tensors pinned-host -> device (int64; a sharded rank copies its relations' edges "
+                    "only), all its typed CSRs / bitmaps / pair tables rebuilt, one train step, loss.item(); wall clock "
+                    "between barriers, max over ranks; bytes summed over ranks"}
 
 
 def main():

@@ -216,6 +216,31 @@ int tipb_neg_sample(uint32_t* mt_state /* [625] */, const uint32_t* stream_words
                     uint32_t* neg_packed /* [n_edges] (row << 16 | col), nullable; n_nodes <= 65535 */,
                     int32_t* status, void* ws, size_t ws_bytes, void* stream);
 
+/* Relation-sharded sampler (one process per GPU).  The accepted MT19937 stream is one global sequence:
+ * relation r starts where relation r-1 (incl. its retries) stopped.  A rank owns the relations [r_lo, r_hi): it holds
+ * only THEIR bitmaps (tipb_neg_bitmap_build_range), scans only their windows, and composes them into ONE table
+ *   rank_table[x] = start offset of relation r_hi if relation r_lo starts at lo(r_lo) + x   (x < w_max; codes < 0: failed)
+ * (shard_begin).  The ranks exchange these tables (all-gather, a few KB; done by the caller, e.g. ncclAllGather),
+ * and shard_end walks the `world` tables to this rank's start offset, materialises the pairs of its relations
+ * (outputs indexed from e_lo = first edge of relation r_lo) and advances mt_state exactly as the unsharded call does on
+ * every rank.  first_rel = device int32 [world + 1]: first relation of every rank.  Same ws for both calls. */
+int tipb_neg_bitmap_build_range(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges,
+                                int64_t n_nodes, int64_t n_rel, int64_t r_lo, int64_t r_hi, int64_t e_lo, int64_t e_hi,
+                                uint32_t* member_local, int32_t* popcount_local /* [r_hi - r_lo] */, void* stream);
+int tipb_neg_sample_shard_begin(const uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words,
+                                const uint32_t* member_local, const int64_t* table, int64_t sum_l, int64_t sum_w,
+                                int64_t n_edges, int64_t n_nodes, int64_t n_rel, int64_t r_lo, int64_t r_hi,
+                                int32_t* rank_table /* [w_max] */, int64_t w_max, void* ws, size_t ws_bytes,
+                                void* stream);
+int tipb_neg_sample_shard_end(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words,
+                              const uint32_t* member_local, const int64_t* range_list, const int64_t* table,
+                              int64_t sum_l, int64_t sum_w, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                              const int32_t* all_tables /* [world, w_max] */, const int32_t* first_rel, int world,
+                              int rank, int64_t w_max, int64_t r_lo, int64_t r_hi, int64_t e_lo, int64_t e_hi,
+                              int64_t* neg_local /* [2, e_hi - e_lo], nullable */,
+                              uint32_t* packed_local /* [e_hi - e_lo], nullable */, int32_t* status, void* ws,
+                              size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- fused pair pass (decoder + loss + gradient)
  * Replaces, for the training step, decoder(pos) / decoder(neg) / the two log-means of src/layers.py:335-340 AND what
  * autograd derives from them, without the typed CSR of the freshly sampled negatives: a pair (i, j, r) is scored once

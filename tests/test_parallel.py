@@ -94,25 +94,28 @@ def _gpu_worker(rank, world, port, out, big=False):
     torch.manual_seed(1111)
     ns.seed(1111, dev)
     settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
-    model = parallel.ShardedTIP(settings, dev, mod="cat", data=data, rank=rank, world=world)
+    model = parallel.ShardedTIP(settings, dev, mod="cat", data=data, rank=rank, world=world,
+                                defer_loss_reduce=(rank >= 0 and big))     # both flavours of the loss exchange
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     losses = []
     for it in range(2):
-        if it == 1:
-            # the graph tensors are overwritten in place (what bench.py's end-to-end loop does every step): the shard's
+        if it == 1 and not big:
+            # this rank's edges are overwritten in place (what bench.py's end-to-end loop does every step): the shard's
             # index structures must be rebuilt and give the same numbers
-            for k in ("dd_train_idx", "dd_train_range", "pp_train_indices", "dp_edge_index"):
-                getattr(model.data, k).copy_(getattr(model.data, k).clone())
-            model.invalidate_graph_caches()
+            model.local_idx.copy_(model.local_idx.clone())
+            model.refresh_shard()
         opt.zero_grad()
         loss = model()
         loss.backward()
-        model.sync_gradients()
         opt.step()
-        losses.append(float(loss.detach()))
+        losses.append(float(model.last_loss) if model.defer_loss_reduce else float(loss.detach()))
     grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters()}
+    neg = model._neg_index.cpu()
+    model.gather_parameters(opt)                      # every rank now holds ALL rows of att / decoder.weight
+    params = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    moments = {n: opt.state[p]["exp_avg"].detach().cpu() for n, p in model.named_parameters()}
     out[rank] = dict(losses=losses, grads=grads, z=model.embeddings.detach().cpu(), block=(model.r_lo, model.r_hi),
-                     neg=model._neg_index.cpu())
+                     edges=(model.e_lo, model.e_hi), neg=neg, params=params, moments=moments)
     dist.destroy_process_group()
 
 
@@ -140,6 +143,8 @@ def test_two_rank_sharding_equals_single_rank(big):
     ref_grads = {n: p.grad.detach().cpu() for n, p in ref.named_parameters()}
     ref_neg = ref._neg_index.cpu()
     ref_z = ref.embeddings.detach().cpu()
+    ref_params = {n: p.detach().cpu() for n, p in ref.named_parameters()}
+    ref_moments = {n: opt.state[p]["exp_avg"].detach().cpu() for n, p in ref.named_parameters()}
 
     world = 2
     mgr = mp.Manager()
@@ -149,7 +154,8 @@ def test_two_rank_sharding_equals_single_rank(big):
     assert set(res) == {0, 1}
     for rank in (0, 1):
         r = res[rank]
-        assert torch.equal(r["neg"], ref_neg), "negative pairs must not depend on the sharding"
+        e_lo, e_hi = r["edges"]
+        assert torch.equal(r["neg"], ref_neg[:, e_lo:e_hi]), "negative pairs must not depend on the sharding"
         np.testing.assert_allclose(r["losses"], ref_losses, rtol=2e-5)
         torch.testing.assert_close(r["z"], ref_z, rtol=1e-4, atol=1e-5)
         lo, hi = r["block"]
@@ -159,3 +165,12 @@ def test_two_rank_sharding_equals_single_rank(big):
                 g, want = g[lo:hi], want[lo:hi]           # relation-local rows live on their owner
             scale = float(want.abs().max()) + 1e-30
             torch.testing.assert_close(g, want, rtol=1e-3, atol=5e-6 * scale, msg=lambda m: f"rank {rank} {n}: {m}")
+        # after gather_parameters every rank holds the single-GPU model (rows of other ranks were stale)
+        for n, p in r["params"].items():
+            scale = float(ref_params[n].abs().max()) + 1e-30
+            torch.testing.assert_close(p, ref_params[n], rtol=2e-3, atol=2e-5 * scale, msg=lambda m: f"rank {rank} param {n}: {m}")
+            scale = float(ref_moments[n].abs().max()) + 1e-30
+            torch.testing.assert_close(r["moments"][n], ref_moments[n], rtol=2e-3, atol=2e-5 * scale,
+                                       msg=lambda m: f"rank {rank} exp_avg {n}: {m}")
+    for n in res[0]["params"]:
+        assert torch.equal(res[0]["params"][n], res[1]["params"][n]), "replicas must be bit-identical after the gather: " + n

@@ -48,6 +48,11 @@ SIGNATURES = {
     "tipb_neg_table_build": (C.c_int, [_p, _p, _i64, _i64, C.c_double, _p, _p]),
     "tipb_neg_sample_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i64]),
     "tipb_neg_sample": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "tipb_neg_bitmap_build_range": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "tipb_neg_sample_shard_begin": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p,
+                                              _sz, _p]),
+    "tipb_neg_sample_shard_end": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _i32, _i32, _i64,
+                                            _i64, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "tipb_pair_pass_supported": (C.c_int, [_i64, _i32]),
     "tipb_pair_chunk": (_i64, []),
     "tipb_pair_workspace_bytes": (_sz, [_i64, _i64, _i32]),

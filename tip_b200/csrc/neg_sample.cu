@@ -196,11 +196,12 @@ __device__ __forceinline__ void write_pair(int64_t* __restrict__ out, uint32_t* 
 //   F  [f_off + x]   = next relation's start offset if this relation starts at lo + x   (x < W; -1: window too short)
 __global__ void __launch_bounds__(1024)
 k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
-              int64_t words_per_rel, const int64_t* __restrict__ table, int* __restrict__ NHI, int* __restrict__ PR,
-              int* __restrict__ F) {
+              int64_t words_per_rel, const int64_t* __restrict__ table, int r_lo, int* __restrict__ NHI,
+              int* __restrict__ PR, int* __restrict__ F) {
+    // `member` holds the bitmaps of the relations [r_lo, ...) only (a rank's shard; r_lo = 0: all relations)
     __shared__ int sw[33];
     __shared__ int s_carry;
-    const int r = blockIdx.x;
+    const int r = r_lo + blockIdx.x;
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), W = int(tb[1]), L = int(tb[2]), k = int(tb[5]);
     const int64_t win_off = tb[3], f_off = tb[4];
@@ -208,7 +209,7 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
         for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = lo + x;
         return;
     }
-    const uint32_t* bits = member + int64_t(r) * words_per_rel;
+    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
     const int n_acc = *n_accepted_ptr;
     if (n_acc <= 0) {  // no usable stream at all
         for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = -1;
@@ -388,9 +389,10 @@ __device__ __forceinline__ int4 chain_row(const int64_t* __restrict__ table, int
 }
 
 __global__ void __launch_bounds__(256)
-k_chain_blocks(const int64_t* __restrict__ table, const int* __restrict__ F, int n_rel, int* __restrict__ G) {
+k_chain_blocks(const int64_t* __restrict__ table, const int* __restrict__ F, int r_lo, int n_rel, int* __restrict__ G) {
+    // blocks of CHAIN_BLOCK relations counted from r_lo; n_rel = end of the range (a rank's shard, or everything)
     __shared__ int4 s_row[CHAIN_BLOCK];
-    const int r0 = blockIdx.y * CHAIN_BLOCK;
+    const int r0 = r_lo + blockIdx.y * CHAIN_BLOCK;
     const int nr = min(CHAIN_BLOCK, n_rel - r0);
     if (threadIdx.x < nr) s_row[threadIdx.x] = chain_row(table, r0 + threadIdx.x);
     __syncthreads();
@@ -469,11 +471,12 @@ __global__ void __launch_bounds__(256)
 k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                    const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                    const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
-                   int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
-    // the block's 256 consecutive draws span very few relations: one thread finds the relation of the first draw
-    // (binary search), every thread then walks forward from it
+                   int r_lo, int64_t e_lo, int64_t e_hi, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
+    // draws [e_lo, e_hi) of the relations [r_lo, ...) (a rank's shard; the outputs are indexed from e_lo and hold
+    // n_edges = e_hi - e_lo pairs).  The block's 256 consecutive draws span very few relations: one thread finds the
+    // relation of the first draw (binary search), every thread then walks forward from it
     __shared__ int s_first;
-    const int64_t e0 = int64_t(blockIdx.x) * blockDim.x;
+    const int64_t e0 = e_lo + int64_t(blockIdx.x) * blockDim.x;
     if (threadIdx.x == 0) {
         int lo_r = 0, hi_r = n_rel - 1;
         while (lo_r < hi_r) {
@@ -484,7 +487,7 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
     }
     __syncthreads();
     const int64_t e = e0 + threadIdx.x;
-    if (e >= n_edges) return;
+    if (e >= e_hi) return;
     int r = s_first;
     while (r + 1 < n_rel && range_list[2 * (r + 1)] <= e) ++r;
     const int64_t start = range_list[2 * r];
@@ -494,7 +497,7 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), k = int(tb[5]);
     const int* nhi = NHI + tb[3];
-    const uint32_t* bits = member + int64_t(r) * words_per_rel;
+    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
     const int i = int(e - start);
     int p = A[o + i];
     if (is_member(bits, p)) {
@@ -503,7 +506,7 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
         const int hits_incl = (i + 1) - (nhi[x0 + i] - rb);
         p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
     }
-    write_pair(out, packed, n_edges, e, p, n_nodes, float(n_nodes));
+    write_pair(out, packed, n_edges, e - e_lo, p, n_nodes, float(n_nodes));
 }
 
 // rounds >= 2, one CTA per relation
@@ -511,16 +514,16 @@ __global__ void __launch_bounds__(256)
 k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                     const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                     const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
-                    int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
-    const int r = blockIdx.x;
+                    int r_lo, int64_t e_lo, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
+    const int r = r_lo + blockIdx.x;
     if (r >= n_rel) return;
     const int o = off[r];
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), k = int(tb[5]);
     if (o < 0 || k == 0) return;
     const int* nhi = NHI + tb[3];
-    const uint32_t* bits = member + int64_t(r) * words_per_rel;
-    const int64_t start = range_list[2 * r];
+    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
+    const int64_t start = range_list[2 * r] - e_lo;
     const int x0 = o - lo;
     const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
     int c_prev = k - (nhi[x0 + k - 1] - rb);  // size of round 1 = hits of round 0
@@ -542,6 +545,106 @@ k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ memb
         __syncthreads();
         s_prev = s_cur;
         c_prev = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Relation-sharded form (one process per GPU): a rank scans only the windows of ITS relations
+// [r_lo, r_hi) and needs its start offset in the shared accepted stream.  The chain is a composition of maps, so
+// every rank composes its own relations into ONE table (k_chain_rank_compose: start offset of relation r_lo -> start
+// offset of relation r_hi, for every candidate offset of r_lo's bracket), the ranks all-gather these tables (a few KB
+// each; the only exchange step of the sampler) and every rank walks the `world` tables (k_chain_resolve).
+// Codes in the tables: >= 0 offset, -1 out of words, -2 left a bracket.
+__device__ __forceinline__ int chain_walk_range(const int64_t* __restrict__ table, const int* __restrict__ F,
+                                                const int* __restrict__ G, int r_begin, int r_end, int block_origin,
+                                                int o) {
+    // relations [r_begin, r_end); blocks of CHAIN_BLOCK counted from block_origin; G is used at block starts whose
+    // bracket holds o, otherwise the block is replayed lookup by lookup.  Returns the offset or a negative code.
+    int r = r_begin;
+    while (r < r_end) {
+        const int4 t = chain_row(table, r);
+        const bool at_block_start = ((r - block_origin) % CHAIN_BLOCK) == 0;
+        const int blk_end = min(r + CHAIN_BLOCK, r_end);
+        const int x = o - t.x;
+        if (at_block_start && x >= 0 && x < t.y) {
+            const int nxt = G[t.z + x];
+            if (nxt < 0) return nxt;
+            o = nxt;
+            r = blk_end;
+        } else {
+            const ChainStep st = chain_advance(t, F, o);
+            if (st.fail) return st.fail == NEG_STATUS_OUT_OF_WORDS ? -1 : -2;
+            o = st.o;
+            ++r;
+        }
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+k_chain_rank_compose(const int64_t* __restrict__ table, const int* __restrict__ F, const int* __restrict__ G, int r_lo,
+                     int r_hi, int w_max, int* __restrict__ rank_table) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w_max) return;
+    if (r_lo >= r_hi) { rank_table[x] = 0; return; }          // a rank without relations: never consulted
+    const int4 t0 = chain_row(table, r_lo);
+    rank_table[x] = x < t0.y ? chain_walk_range(table, F, G, r_lo, r_hi, r_lo, t0.x + x) : -2;
+}
+
+// one CTA: thread 0 walks the ranks' tables, then this rank's blocks; thread b replays block b to emit off[]
+__global__ void __launch_bounds__(CHAIN_MAX_BLOCKS)
+k_chain_resolve(const int64_t* __restrict__ table, const int* __restrict__ F, const int* __restrict__ G,
+                const int* __restrict__ all_tables, const int* __restrict__ first_rel, int world, int rank, int w_max,
+                int* __restrict__ off, int* __restrict__ chain_out, int* __restrict__ status) {
+    __shared__ int s_start[CHAIN_MAX_BLOCKS + 1];
+    __shared__ int s_fail;
+    const int r_lo = first_rel[rank], r_hi = first_rel[rank + 1];
+    const int nb = (r_hi - r_lo + CHAIN_BLOCK - 1) / CHAIN_BLOCK;
+    if (threadIdx.x == 0) {
+        int o = 0, mine = 0, fail = 0;
+        for (int k = 0; k < world && !fail; ++k) {
+            if (k == rank) mine = o;
+            const int a = first_rel[k], b = first_rel[k + 1];
+            if (a >= b) continue;
+            const int4 t0 = chain_row(table, a);
+            const int x = o - t0.x;
+            if (x < 0 || x >= t0.y || x >= w_max) { fail = NEG_STATUS_BRACKET_MISS; break; }
+            const int nxt = all_tables[int64_t(k) * w_max + x];
+            if (nxt < 0) { fail = nxt == -1 ? NEG_STATUS_OUT_OF_WORDS : NEG_STATUS_BRACKET_MISS; break; }
+            o = nxt;
+        }
+        s_fail = fail;
+        if (fail) {
+            atomicOr(status, fail);
+        } else {
+            chain_out[0] = o;                                   // accepted values consumed by ALL ranks' relations
+            int oo = mine;
+            for (int b = 0; b < nb; ++b) {                      // start offsets of this rank's blocks
+                s_start[b] = oo;
+                const int rb = r_lo + b * CHAIN_BLOCK;
+                oo = chain_walk_range(table, F, G, rb, min(rb + CHAIN_BLOCK, r_hi), r_lo, oo);
+                if (oo < 0) { oo = 0; }                         // cannot happen: the same lookups composed the rank table
+            }
+        }
+    }
+    __syncthreads();
+    const int b = threadIdx.x;
+    if (b >= nb) return;
+    const int r0 = r_lo + b * CHAIN_BLOCK, r1 = min(r0 + CHAIN_BLOCK, r_hi);
+    if (s_fail) {
+        for (int r = r0; r < r1; ++r) off[r] = -1;
+        return;
+    }
+    int o = s_start[b];
+    for (int r = r0; r < r1; ++r) {
+        off[r] = o;
+        const ChainStep st = chain_advance(chain_row(table, r), F, o);
+        if (st.fail) {                                           // (unreachable for the same reason)
+            atomicOr(status, st.fail);
+            for (int q = r + 1; q < r1; ++q) off[q] = -1;
+            return;
+        }
+        o = st.o;
     }
 }
 
@@ -670,10 +773,11 @@ k_finalize(const uint32_t* __restrict__ U, const int* __restrict__ Apos, const i
 }
 
 __global__ void k_bitmap_build(const int64_t* __restrict__ pos_edge_index, const int64_t* __restrict__ range_list,
-                               int64_t n_edges, int n_nodes, int n_rel, int64_t words_per_rel,
-                               uint32_t* __restrict__ member) {
-    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
+                               int64_t n_edges, int n_nodes, int n_rel, int64_t words_per_rel, int r_lo, int64_t e_lo,
+                               int64_t e_hi, uint32_t* __restrict__ member) {
+    // edges [e_lo, e_hi) = the relations [r_lo, ...) whose bitmaps `member` holds (a rank's shard; 0 / n_edges: all)
+    int64_t e = e_lo + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= e_hi) return;
     int lo = 0, hi = n_rel - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -683,7 +787,7 @@ __global__ void k_bitmap_build(const int64_t* __restrict__ pos_edge_index, const
     const int64_t a = pos_edge_index[e], b = pos_edge_index[n_edges + e];
     if (a < 0 || a >= n_nodes || b < 0 || b >= n_nodes) return;
     const int64_t key = a * n_nodes + b;
-    atomicOr(&member[int64_t(lo) * words_per_rel + (key >> 5)], 1u << (key & 31));
+    atomicOr(&member[int64_t(lo - r_lo) * words_per_rel + (key >> 5)], 1u << (key & 31));
 }
 
 __global__ void __launch_bounds__(256)
@@ -765,14 +869,25 @@ size_t tipb_neg_bitmap_bytes(int64_t n_nodes, int64_t n_rel) { return size_t(bit
 
 int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges, int64_t n_nodes,
                           int64_t n_rel, uint32_t* member, int32_t* popcount, void* stream) {
+    return tipb_neg_bitmap_build_range(pos_edge_index, range_list, n_edges, n_nodes, n_rel, 0, n_rel, 0, n_edges, member,
+                                       popcount, stream);
+}
+
+int tipb_neg_bitmap_build_range(const int64_t* pos_edge_index, const int64_t* range_list, int64_t n_edges,
+                                int64_t n_nodes, int64_t n_rel, int64_t r_lo, int64_t r_hi, int64_t e_lo, int64_t e_hi,
+                                uint32_t* member, int32_t* popcount, void* stream) {
     TIPB_CHECK_ARG(range_list && member && popcount && (n_edges == 0 || pos_edge_index), "neg_bitmap_build: NULL argument");
     TIPB_CHECK_ARG(n_nodes > 0 && n_nodes <= 46340, "neg_bitmap_build: n_nodes^2 must fit in int32");
+    TIPB_CHECK_ARG(0 <= r_lo && r_lo <= r_hi && r_hi <= n_rel && 0 <= e_lo && e_lo <= e_hi && e_hi <= n_edges,
+                   "neg_bitmap_build: bad relation / edge range");
     cudaStream_t s = (cudaStream_t)stream;
-    TIPB_CHECK_CUDA(cudaMemsetAsync(member, 0, tipb_neg_bitmap_bytes(n_nodes, n_rel), s));
-    if (n_edges > 0)
-        k_bitmap_build<<<(unsigned)ceil_div(n_edges, 256), 256, 0, s>>>(pos_edge_index, range_list, n_edges, (int)n_nodes,
-                                                                        (int)n_rel, bitmap_words(n_nodes), member);
-    if (n_rel > 0) k_bitmap_popcount<<<(unsigned)n_rel, 256, 0, s>>>(member, bitmap_words(n_nodes), popcount);
+    const int64_t n_local = r_hi - r_lo;
+    TIPB_CHECK_CUDA(cudaMemsetAsync(member, 0, tipb_neg_bitmap_bytes(n_nodes, n_local > 0 ? n_local : 1), s));
+    if (e_hi > e_lo)
+        k_bitmap_build<<<(unsigned)ceil_div(e_hi - e_lo, 256), 256, 0, s>>>(pos_edge_index, range_list, n_edges, (int)n_nodes,
+                                                                            (int)n_rel, bitmap_words(n_nodes), (int)r_lo,
+                                                                            e_lo, e_hi, member);
+    if (n_local > 0) k_bitmap_popcount<<<(unsigned)n_local, 256, 0, s>>>(member, bitmap_words(n_nodes), popcount);
     TIPB_CHECK_LAUNCH("neg_bitmap_build");
     return TIPB_OK;
 }
@@ -864,12 +979,12 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index, neg_packed);
     } else {
-        k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, w.NHI, w.PR, w.F);
+        k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, 0, w.NHI, w.PR, w.F);
         const int n_blocks = int(ceil_div(n_rel, CHAIN_BLOCK));
         if (n_blocks <= CHAIN_MAX_BLOCKS && size_t(n_rel) * sizeof(int4) <= 160 * 1024) {
             const size_t tsm = size_t(n_rel) * sizeof(int4);
             if ((rc = ensure_dyn_smem((const void*)k_chain_stitch, tsm))) return rc;
-            k_chain_blocks<<<dim3(16, (unsigned)n_blocks), T, 0, s>>>(table, w.F, (int)n_rel, w.G);
+            k_chain_blocks<<<dim3(16, (unsigned)n_blocks), T, 0, s>>>(table, w.F, 0, (int)n_rel, w.G);
             k_chain_stitch<<<1, CHAIN_MAX_BLOCKS, tsm, s>>>(table, w.F, w.G, (int)n_rel, w.off, w.chain_out, call_status);
         } else {
             const size_t smem = size_t(n_rel) * 20 + size_t((WALK_AHEAD + 1) * WALK_WIN + 16) * sizeof(int);
@@ -878,14 +993,101 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         }
         if (n_edges > 0)
             k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
-                                                                           w.NHI, (int)n_rel, (int)n_nodes, n_edges,
-                                                                           neg_edge_index, neg_packed);
-        k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
-                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges,
-                                                                            neg_edge_index, neg_packed);
+                                                                           w.NHI, (int)n_rel, (int)n_nodes, n_edges, 0,
+                                                                           0, n_edges, neg_edge_index, neg_packed);
+        k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off, w.NHI, (int)n_rel,
+                                                          (int)n_nodes, n_edges, 0, 0, neg_edge_index, neg_packed);
     }
     k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, call_status, status, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");
+    return TIPB_OK;
+}
+
+// ---- relation-sharded sampler: begin (own windows + own rank table) ... all-gather by the caller ... end
+static int shard_check(const char* who, int64_t n_rel, int64_t r_lo, int64_t r_hi, int64_t w_max) {
+    if (!(0 <= r_lo && r_lo <= r_hi && r_hi <= n_rel) || w_max < 1 || w_max > (int64_t(1) << 28)) {
+        set_last_error("%s: bad relation range [%lld, %lld) of %lld or w_max", who, (long long)r_lo, (long long)r_hi,
+                       (long long)n_rel);
+        return TIPB_ERR_INVALID_ARGUMENT;
+    }
+    if ((r_hi - r_lo + CHAIN_BLOCK - 1) / CHAIN_BLOCK > CHAIN_MAX_BLOCKS) {
+        set_last_error("%s: more than %d relations per rank", who, CHAIN_BLOCK * CHAIN_MAX_BLOCKS);
+        return TIPB_ERR_UNSUPPORTED;
+    }
+    return TIPB_OK;
+}
+
+int tipb_neg_sample_shard_begin(const uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words,
+                                const uint32_t* member_local, const int64_t* table, int64_t sum_l, int64_t sum_w,
+                                int64_t n_edges, int64_t n_nodes, int64_t n_rel, int64_t r_lo, int64_t r_hi,
+                                int32_t* rank_table, int64_t w_max, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(mt_state && stream_words && member_local && table && rank_table && ws, "neg_sample_shard_begin: NULL argument");
+    TIPB_CHECK_ARG(n_nodes > 1 && n_nodes <= 46340, "neg_sample_shard_begin: n_nodes must be in [2, 46340]");
+    TIPB_CHECK_ARG(n_words > MT_N && n_words < (int64_t(1) << 31) - 4096, "neg_sample_shard_begin: bad stream length");
+    TIPB_CHECK_ARG((reinterpret_cast<uintptr_t>(stream_words) & 15) == 0, "neg_sample_shard_begin: stream_words must be 16-byte aligned");
+    TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
+                   "neg_sample_shard_begin: workspace too small");
+    if (int rc = shard_check("neg_sample_shard_begin", n_rel, r_lo, r_hi, w_max)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    NegWs w;
+    neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, ws, &w);
+    const uint32_t max_val = uint32_t(n_nodes * n_nodes - 1);
+    uint32_t mask = 1;
+    while (mask < max_val) mask = (mask << 1) | 1u;
+    const int64_t wpr = bitmap_words(n_nodes);
+    int rc;
+    TIPB_CHECK_CUDA(cudaMemsetAsync(w.call_status, 0, sizeof(int32_t), s));
+    const int64_t n_chunks = ceil_div(n_words, ACC_CHUNK);
+    k_accept_count<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
+    if ((rc = exclusive_scan_i32(w.flags, w.flags, n_chunks, w.scan_ws, s))) return rc;
+    k_compact<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
+                                                         w.A, w.Apos);
+    const int* n_acc = w.flags + n_chunks;
+    const int64_t n_local = r_hi - r_lo;
+    if (n_local > 0) {
+        k_window_scan<<<(unsigned)n_local, 1024, 0, s>>>(w.A, n_acc, member_local, wpr, table, (int)r_lo, w.NHI, w.PR, w.F);
+        const int n_blocks = int(ceil_div(n_local, CHAIN_BLOCK));
+        k_chain_blocks<<<dim3(16, (unsigned)n_blocks), 256, 0, s>>>(table, w.F, (int)r_lo, (int)r_hi, w.G);
+    }
+    k_chain_rank_compose<<<(unsigned)ceil_div(w_max, 256), 256, 0, s>>>(table, w.F, w.G, (int)r_lo, (int)r_hi, (int)w_max,
+                                                                       rank_table);
+    TIPB_CHECK_LAUNCH("neg_sample_shard_begin");
+    return TIPB_OK;
+}
+
+int tipb_neg_sample_shard_end(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words,
+                              const uint32_t* member_local, const int64_t* range_list, const int64_t* table,
+                              int64_t sum_l, int64_t sum_w, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                              const int32_t* all_tables, const int32_t* first_rel, int world, int rank, int64_t w_max,
+                              int64_t r_lo, int64_t r_hi, int64_t e_lo, int64_t e_hi, int64_t* neg_local,
+                              uint32_t* packed_local, int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+    TIPB_CHECK_ARG(mt_state && stream_words && member_local && range_list && table && all_tables && first_rel && status && ws,
+                   "neg_sample_shard_end: NULL argument");
+    TIPB_CHECK_ARG(neg_local || packed_local, "neg_sample_shard_end: no output");
+    TIPB_CHECK_ARG(!packed_local || n_nodes <= 65535, "neg_sample_shard_end: the packed output holds 16-bit node ids");
+    TIPB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && 0 <= e_lo && e_lo <= e_hi && e_hi <= n_edges,
+                   "neg_sample_shard_end: bad rank / edge range");
+    if (int rc = shard_check("neg_sample_shard_end", n_rel, r_lo, r_hi, w_max)) return rc;
+    TIPB_CHECK_ARG(ws_bytes >= neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, nullptr, nullptr),
+                   "neg_sample_shard_end: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    NegWs w;
+    neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, ws, &w);
+    const int64_t wpr = bitmap_words(n_nodes);
+    // the relation range is read on the device from first_rel; the host passes the matching edge range
+    k_chain_resolve<<<1, CHAIN_MAX_BLOCKS, 0, s>>>(table, w.F, w.G, all_tables, first_rel, world, rank, (int)w_max, w.off,
+                                                   w.chain_out, w.call_status);
+    const int64_t e_local = e_hi - e_lo;      // = the edges of the relations [r_lo, r_hi) = first_rel[rank .. rank + 1]
+    if (e_local > 0)
+        k_materialize_main<<<(unsigned)ceil_div(e_local, 256), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off,
+                                                                           w.NHI, (int)n_rel, (int)n_nodes, e_local,
+                                                                           (int)r_lo, e_lo, e_hi, neg_local, packed_local);
+    if (r_hi > r_lo)
+        k_materialize_fixup<<<(unsigned)(r_hi - r_lo), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off, w.NHI,
+                                                                  (int)r_hi, (int)n_nodes, e_local, (int)r_lo, e_lo,
+                                                                  neg_local, packed_local);
+    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, w.call_status, status, mt_state);
+    TIPB_CHECK_LAUNCH("neg_sample_shard_end");
     return TIPB_OK;
 }
 }

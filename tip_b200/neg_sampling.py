@@ -275,7 +275,7 @@ def last_status(device=None, clear=True):
     cannot be overwritten by later steps.  One host synchronisation; `clear` resets the words after reading."""
     device = _device_of(device)
     code = 0
-    for m in _member_cache.values():
+    for m in list(_member_cache.values()) + list(_sharded_samplers):
         if m.status.device == device:
             code |= int(m.status.item())
             if clear:
@@ -288,3 +288,148 @@ def negative_sampling(pos_edge_index, num_nodes):
     e = pos_edge_index.shape[1]
     rl = torch.tensor([[0, e]], dtype=torch.long, device=pos_edge_index.device)
     return typed_negative_sampling(pos_edge_index, num_nodes, rl)
+
+
+# =============================================================================== relation-sharded sampler
+import weakref
+
+_sharded_samplers = weakref.WeakSet()
+
+
+class ShardedSampler(object):
+    """typed_negative_sampling for ONE rank of a relation-sharded run (tip_b200/parallel.py).
+
+    The accepted MT19937 stream is one global sequence, so the negatives of a relation depend on how many values
+    all earlier relations consumed.  A rank holds the bitmaps of ITS relations only, scans only their windows and
+    composes them into one table (its start offset -> the next rank's start offset); the ranks all-gather these
+    tables (a few KB: the only exchange step), walk them to their own start offset and materialise their pairs.
+    Every rank advances the same MT19937 state, so the result is bit for bit the slice [e_lo, e_hi) of what the
+    unsharded sampler -- and the reference, src/neg_sampling.py:22-26 -- produces.
+
+    `local_idx` / `local_range`: the edges and ranges (counted from 0) of the relations [r_lo, r_hi);
+    `rl_host`: the FULL cumulative range table on the host; `first_rel`: first relation of every rank (+ n_rel);
+    `coll`: object with all_gather_(out [world, n], inp [n]) and all_reduce_max_(t) (see parallel._Collective)."""
+
+    def __init__(self, local_idx, num_nodes, local_range, rl_host, first_rel, rank, world, coll):
+        L = lib()
+        dev = local_idx.device
+        self.device, self.num_nodes, self.rank, self.world, self.coll = dev, int(num_nodes), int(rank), int(world), coll
+        self.rl_host = np.ascontiguousarray(np.asarray(rl_host, dtype=np.int64))
+        self.first_rel_host = [int(v) for v in first_rel]
+        self.n_rel = int(self.rl_host.shape[0])
+        self.r_lo, self.r_hi = self.first_rel_host[rank], self.first_rel_host[rank + 1]
+        self.n_local = self.r_hi - self.r_lo
+        self.n_edges = int(self.rl_host[-1, 1]) if self.n_rel else 0
+        self.e_lo = int(self.rl_host[self.r_lo, 0]) if self.n_local else 0
+        self.e_hi = int(self.rl_host[self.r_hi - 1, 1]) if self.n_local else 0
+        assert int(local_idx.shape[1]) == self.e_hi - self.e_lo
+        self.range_dev = torch.from_numpy(self.rl_host).to(dev)
+        self.first_rel = torch.tensor(self.first_rel_host, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.z_sigma = Z_SIGMA
+        self.member = None
+        self._pop_all = None
+        _sharded_samplers.add(self)
+        with torch.cuda.device(dev):
+            self.rebuild(local_idx, local_range)
+
+    def rebuild(self, local_idx, local_range):
+        """bitmaps of the own relations (device), their popcounts exchanged once, bracket table on the host"""
+        L = lib()
+        dev = self.device
+        nbytes = L.tipb_neg_bitmap_bytes(self.num_nodes, max(self.n_local, 1))
+        if nbytes > (24 << 30):
+            raise _lib.TipbError(f"positive-pair bitmaps of this rank would need {nbytes >> 30} GiB")
+        if self.member is None or self.member.numel() != max(nbytes // 4, 1):
+            self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)
+        n_pad = max(max(b - a for a, b in zip(self.first_rel_host[:-1], self.first_rel_host[1:])), 1)
+        pop_local = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+        lr = _i64c(local_range.to(device=dev, dtype=torch.long))
+        if self.n_local:
+            check(L.tipb_neg_bitmap_build(ptr(_i64c(local_idx)), ptr(lr), int(local_idx.shape[1]), self.num_nodes,
+                                          self.n_local, ptr(self.member), ptr(pop_local), stream()), "neg_bitmap_build")
+        pop_all = torch.zeros((self.world, n_pad), dtype=torch.int32, device=dev)
+        self.coll.all_gather_(pop_all, pop_local)
+        pop_all = pop_all.cpu().numpy()
+        self._pop_all = np.concatenate([pop_all[k, : self.first_rel_host[k + 1] - self.first_rel_host[k]]
+                                        for k in range(self.world)]).astype(np.int32) if self.n_rel else np.zeros(1, np.int32)
+        self._build_table()
+
+    def _build_table(self):
+        L = lib()
+        table = np.zeros((max(self.n_rel, 1), 7), dtype=np.int64)
+        totals = np.zeros(4, dtype=np.int64)
+        pop = np.ascontiguousarray(self._pop_all)
+        check(L.tipb_neg_table_build(self.rl_host.ctypes.data_as(C.c_void_p), pop.ctypes.data_as(C.c_void_p), self.n_rel,
+                                     self.num_nodes, self.z_sigma, table.ctypes.data_as(C.c_void_p),
+                                     totals.ctypes.data_as(C.c_void_p)), "neg_table_build")
+        self.table = torch.from_numpy(table).to(self.device)
+        self.sum_l, self.sum_w, max_index = int(totals[0]), int(totals[1]), int(totals[2])
+        firsts = [a for a, b in zip(self.first_rel_host[:-1], self.first_rel_host[1:]) if b > a]
+        self.w_max = int(max([int(table[a, 1]) for a in firsts] + [1]))
+        self.rank_table = torch.empty(self.w_max, dtype=torch.int32, device=self.device)
+        self.all_tables = torch.empty((self.world, self.w_max), dtype=torch.int32, device=self.device)
+        bits = max(int(self.num_nodes * self.num_nodes - 1).bit_length(), 1)
+        p_accept = float(self.num_nodes) ** 2 / float(1 << bits)
+        need = max_index / p_accept
+        self.n_new = int(need + Z_SIGMA * np.sqrt(need * (1.0 - p_accept) / p_accept + 1.0) + 4096)
+
+    def sample(self, out=None, packed_out=None, check_status=True):
+        """negatives of this rank's relations: int64 [2, E_local] and / or packed int32 [E_local]"""
+        with torch.cuda.device(self.device):
+            return self._sample(out, packed_out, check_status)
+
+    def _sample(self, out, packed_out, check_status):
+        L = lib()
+        dev = self.device
+        e_local = self.e_hi - self.e_lo
+        if packed_out is None and out is None:
+            out = torch.empty((2, e_local), dtype=torch.long, device=dev)
+        if self.n_edges == 0:
+            return out if out is not None else packed_out
+        result = out if out is not None else packed_out
+        if e_local == 0:            # a rank without relations still takes part in the exchange and advances the stream
+            out, packed_out = torch.empty((2, 1), dtype=torch.long, device=dev), None
+        rng = _get_rng(dev)
+        if check_status:
+            pending = int(self.status.item())
+            if pending:
+                self.status.zero_()
+                raise _lib.TipbError(f"negative sampling: an earlier unchecked call failed (status {pending})")
+        while True:
+            rng.join()
+            if not rng.valid or rng.n_new < self.n_new:
+                rng.generate(max(self.n_new, rng.n_new))
+                rng.valid = True
+            n_words = 624 + rng.n_new
+            ws = workspace(L.tipb_neg_sample_workspace_bytes(self.n_edges, self.n_rel, n_words, self.sum_l, self.sum_w), dev, "neg")
+            check(L.tipb_neg_sample_shard_begin(ptr(rng.state), ptr(rng.words), n_words, ptr(self.member), ptr(self.table),
+                                                self.sum_l, self.sum_w, self.n_edges, self.num_nodes, self.n_rel, self.r_lo,
+                                                self.r_hi, ptr(self.rank_table), self.w_max, ptr(ws), ws.numel(), stream()),
+                  "neg_sample_shard_begin")
+            self.coll.all_gather_(self.all_tables, self.rank_table)          # the sampler's only exchange step
+            check(L.tipb_neg_sample_shard_end(ptr(rng.state), ptr(rng.words), n_words, ptr(self.member), ptr(self.range_dev),
+                                              ptr(self.table), self.sum_l, self.sum_w, self.n_edges, self.num_nodes,
+                                              self.n_rel, ptr(self.all_tables), ptr(self.first_rel), self.world, self.rank,
+                                              self.w_max, self.r_lo, self.r_hi, self.e_lo, self.e_hi, ptr(out),
+                                              ptr(packed_out), ptr(self.status), ptr(ws), ws.numel(), stream()),
+                  "neg_sample_shard_end")
+            code = int(self.status.item()) if check_status else 0
+            if code == 0:
+                rng.valid = False
+                break
+            # every rank walked the same tables and saw the same failure; the state was left untouched: retry
+            self.status.zero_()
+            if code & 4:
+                self.z_sigma *= 2.0                   # an offset left its bracket: widen all brackets (same on every rank)
+                self._build_table()
+            if code & 1:
+                self.n_new = self.n_new * 2
+        if _prefetch:
+            cur = torch.cuda.current_stream(dev)
+            rng.side.wait_stream(cur)
+            with torch.cuda.stream(rng.side):
+                rng.generate(max(self.n_new, rng.n_new))
+            rng.valid = True
+            rng.forked = True
+        return result
