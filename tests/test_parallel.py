@@ -115,7 +115,8 @@ def _gpu_worker(rank, world, port, out, big=False):
     params = {n: p.detach().cpu() for n, p in model.named_parameters()}
     moments = {n: opt.state[p]["exp_avg"].detach().cpu() for n, p in model.named_parameters()}
     out[rank] = dict(losses=losses, grads=grads, z=model.embeddings.detach().cpu(), block=(model.r_lo, model.r_hi),
-                     edges=(model.e_lo, model.e_hi), neg=neg, params=params, moments=moments)
+                     edges=(model.e_lo, model.e_hi), neg=neg, params=params, moments=moments,
+                     test_neg=model.test_neg_index.cpu())
     dist.destroy_process_group()
 
 
@@ -156,6 +157,7 @@ def test_two_rank_sharding_equals_single_rank(big):
         r = res[rank]
         e_lo, e_hi = r["edges"]
         assert torch.equal(r["neg"], ref_neg[:, e_lo:e_hi]), "negative pairs must not depend on the sharding"
+        assert torch.equal(r["test_neg"], ref.test_neg_index.cpu()), "test-set negatives (drawn first from the same stream)"
         np.testing.assert_allclose(r["losses"], ref_losses, rtol=2e-5)
         torch.testing.assert_close(r["z"], ref_z, rtol=1e-4, atol=1e-5)
         lo, hi = r["block"]

@@ -354,8 +354,11 @@ class TIP(nn.Module):
         data = _Data(data_dict, self.device)
         data.dd_train_range = data.dd_train_range.to(torch.long)
         data.dd_test_range = data.dd_test_range.to(torch.long)
-        self.test_neg_index = typed_negative_sampling(data.dd_test_idx, data.n_drug, data.dd_test_range)
+        self.test_neg_index = self._sample_test_negatives(data)      # src/layers.py:293 (drawn before the model exists)
         return data
+
+    def _sample_test_negatives(self, data):
+        return typed_negative_sampling(data.dd_test_idx, data.n_drug, data.dd_test_range)
 
     def _prepare_model(self):
         d, s = self.data, self.settings

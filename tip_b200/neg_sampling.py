@@ -22,6 +22,7 @@ from . import _lib
 from ._lib import check, lib, ptr, stream
 from .ops import _i64c, workspace
 
+BITMAP_LIMIT_GIB = 64  # per device; 10^4 drugs x 4000 relations = 50 GB unsharded, 6 GB per rank on 8 GPUs
 Z_SIGMA = 7.0          # half-width of the offset brackets, in standard deviations of the retry-count model
 _member_cache = {}     # positive-pair bitmaps + bracket tables, keyed on the identity of (pos_edge_index, range_list)
 _rng = {}              # device index -> _DeviceRng
@@ -160,8 +161,9 @@ class _Membership(object):
                                and rl[-1, 1] == self.n_edges):
             raise ValueError("range_list must be the cumulative [start,end) table of src/utils.py:26-32")
         nbytes = L.tipb_neg_bitmap_bytes(num_nodes, max(self.n_rel, 1))
-        if nbytes > (24 << 30):
-            raise _lib.TipbError(f"positive-pair bitmaps would need {nbytes >> 30} GiB")
+        if nbytes > (BITMAP_LIMIT_GIB << 30):
+            raise _lib.TipbError(f"positive-pair bitmaps would need {nbytes >> 30} GiB (shard the relations over more "
+                                 "ranks: tip_b200.parallel)")
         if self.member is None or self.member.numel() != max(nbytes // 4, 1):
             self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)
         popcount = torch.zeros(max(self.n_rel, 1), dtype=torch.int32, device=dev)
@@ -338,7 +340,7 @@ class ShardedSampler(object):
         L = lib()
         dev = self.device
         nbytes = L.tipb_neg_bitmap_bytes(self.num_nodes, max(self.n_local, 1))
-        if nbytes > (24 << 30):
+        if nbytes > (BITMAP_LIMIT_GIB << 30):
             raise _lib.TipbError(f"positive-pair bitmaps of this rank would need {nbytes >> 30} GiB")
         if self.member is None or self.member.numel() != max(nbytes // 4, 1):
             self.member = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=dev)

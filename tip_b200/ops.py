@@ -482,7 +482,12 @@ class PairPlan(object):
         self.n_edges = int(edge_index.shape[1])
         rl_dev = _i64c(range_list.to(device=dev, dtype=torch.long))
         rl = np.ascontiguousarray(rl_dev.cpu().numpy() if rl_host is None else np.asarray(rl_host, dtype=np.int64))
-        chunk = int(L.tipb_pair_chunk())
+        # work-item size: ~3 items per resident CTA slot (2 per SM) so that the largest-first schedule has no long tail
+        # (a rank of a sharded run owns few relations), whole tiles of 2048 pairs, at most the library's chunk
+        chunk_max = int(L.tipb_pair_chunk())
+        slots = 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+        total_pairs = int(rl[-1, 1]) * 3 // 2 if rl.shape[0] else 0          # E/2 positive + E negative pairs
+        chunk = min(chunk_max, max(2048, -(-total_pairs // (3 * slots * 2048)) * 2048))
         key = (rl.tobytes(), chunk, str(dev))
         tables = _item_tables.get(key)
         if tables is None:

@@ -167,6 +167,32 @@ class ShardedTIP(TIP):
         super().__init__(settings, device, mod=mod, data_path=data_path, data=data)
 
     # ---- data: the base class moved everything to the device; derive this rank's shard
+    def _sample_test_negatives(self, data):
+        """src/layers.py:293 sharded: the test-set negatives are drawn from the same global stream, every rank samples
+        the relations it owns (bitmaps of its relations only) and the slices are exchanged once"""
+        if self.world == 1:
+            return super()._sample_test_negatives(data)
+        rl = np.ascontiguousarray(data.dd_test_range.cpu().numpy().astype(np.int64))
+        blocks = partition_relations(rl, self.world)
+        first = [b[0] for b in blocks] + [int(rl.shape[0])]
+        r_lo, r_hi = blocks[self.rank]
+        e_lo = int(rl[r_lo, 0]) if r_hi > r_lo else 0
+        e_hi = int(rl[r_hi - 1, 1]) if r_hi > r_lo else 0
+        local_idx = data.dd_test_idx[:, e_lo:e_hi].contiguous()
+        local_rl = torch.from_numpy(np.ascontiguousarray(rl[r_lo:r_hi] - e_lo)).to(self.device)
+        sampler = _ns.ShardedSampler(local_idx, data.n_drug, local_rl, rl, first, self.rank, self.world, self.coll)
+        mine = sampler.sample()
+        sizes = [int(rl[b - 1, 1]) - int(rl[a, 0]) if b > a else 0 for a, b in blocks]
+        pad = max(max(sizes), 1)
+        send = torch.zeros(2 * pad, dtype=torch.long, device=self.device)
+        send[:mine.shape[1]] = mine[0]
+        send[pad:pad + mine.shape[1]] = mine[1]
+        recv = torch.zeros((self.world, 2 * pad), dtype=torch.long, device=self.device)
+        self.coll.all_gather_(recv, send)
+        out = torch.cat([torch.stack([recv[k, :n], recv[k, pad:pad + n]]) for k, n in enumerate(sizes)], dim=1)
+        del sampler
+        return out
+
     def _prepare_model(self):
         d = self.data
         self.rl_host = np.ascontiguousarray(d.dd_train_range.cpu().numpy().astype(np.int64))

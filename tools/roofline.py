@@ -17,6 +17,7 @@ FAMILIES = [
     ("negative sampler", r"k_accept_count|k_compact|k_window_scan|k_chain_|k_materialize|k_finalize|k_mt_"),
     ("negative plan build", r"k_grp_|k_csr_|k_rel_order|k_scan_lookback|k_sort_"),
     ("Adam", r"k_adam"),
+    ("collectives (NCCL kernels, incl. waiting for the peers)", r"nccl|ncclDevKernel"),
 ]
 
 
