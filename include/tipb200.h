@@ -166,6 +166,9 @@ int tipb_edges_mirrored(const int64_t* edge_index, const int64_t* range_list, in
 /* all n_nodes^2 x n_rel scores (BASELINE.json config 5): out[r,i,j] */
 int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim,
                        int apply_sigmoid, float* out, void* stream);
+/* 0 = every tensor-core sweep so far ran its barrier protocol to the end (the waits are bounded: a protocol fault shows
+ * up here instead of as a hang); synchronises the device, clears the flag */
+int tipb_decoder_sweep_status(void);
 
 /* ---------------------------------------------------------------- typed negative sampling
  * Replaces typed_negative_sampling (src/neg_sampling.py:5-26) bit for bit, including the legacy

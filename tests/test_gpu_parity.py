@@ -718,11 +718,13 @@ def test_fused_adam_matches_torch_adam():
         optim.Adam([cpu_p], lr=0.1).step()
 
 
-@pytest.mark.parametrize("n,r,dim", [(645, 5, 16), (97, 3, 8), (130, 2, 32), (64, 2, 4), (129, 3, 12), (3000, 1, 16)])
+@pytest.mark.parametrize("n,r,dim", [(645, 5, 16), (645, 120, 16), (97, 3, 8), (768, 2, 16), (130, 2, 32), (64, 2, 4),
+                                     (129, 3, 12), (3000, 1, 16)])
 def test_decoder_sweep_all_widths(n, r, dim):
-    """BASELINE.json config 5 kernel: the register-tiled sweep (dim in {4, 8, 16, 32}, z in shared memory), and the
-    generic kernel for other widths / larger graphs, against a float64 einsum"""
-    from tip_b200 import ops
+    """BASELINE.json config 5 kernel: the tcgen05 sweep (dim 8 / 16, up to 768 nodes: bf16x3-split GEMM with TMEM
+    accumulators; (645, 120, 16) runs every persistent CTA over several tiles), the register-tiled CUDA-core sweep
+    (other widths) and the generic kernel (larger graphs), against a float64 einsum"""
+    from tip_b200 import _lib, ops
     d = dev()
     torch.manual_seed(n + dim)
     z, w = torch.randn(n, dim), torch.randn(r, dim) * 0.5
@@ -731,6 +733,7 @@ def test_decoder_sweep_all_widths(n, r, dim):
     assert tuple(out.shape) == (r, n, n)
     close(out, ref, what="sweep values")
     close(ops.decoder_sweep(z.to(d), w.to(d), sigmoid=True), torch.sigmoid(ref), what="sweep scores")
+    assert _lib.lib().tipb_decoder_sweep_status() == 0, "a barrier wait of the tensor-core sweep timed out"
 
 
 # =============================================================================== the benched workload itself

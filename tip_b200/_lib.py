@@ -43,6 +43,7 @@ SIGNATURES = {
     "tipb_decoder_bce_fused_mirrored": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "tipb_edges_mirrored": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),
     "tipb_decoder_sweep": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
+    "tipb_decoder_sweep_status": (C.c_int, []),
     "tipb_neg_bitmap_bytes": (_sz, [_i64, _i64]),
     "tipb_neg_bitmap_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "tipb_neg_table_build": (C.c_int, [_p, _p, _i64, _i64, C.c_double, _p, _p]),

@@ -139,6 +139,12 @@ size_t scan_ws_bytes(int64_t n);
 // exclusive scan of in[0..n) into out[0..n); out[n] (one past) receives the total.  in may alias out.
 int exclusive_scan_i32(const int* in, int* out, int64_t n, void* ws, cudaStream_t s);
 
+// tensor-core decoder sweep (sweep_tc.cu)
+bool sweep_tc_supported(int64_t n_nodes, int64_t n_rel, int dim);
+int sweep_tc_run(const float* z, const float* w, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid, float* out,
+                 cudaStream_t s);
+int* sweep_tc_error_flag();
+
 size_t sort_ws_bytes(int64_t n);
 // stable LSD radix sort of (key,val) pairs on the low `key_bits` bits of key.  Result lands in
 // (keys_out, vals_out); (keys_in, vals_in) are clobbered.

@@ -15,6 +15,8 @@
 // from which  d_z[n] = sum_{s in node n} w[rel_s] * acc[s]   (node-major reduction) and
 //             d_w[r] = 1/2 sum_{s: rel_s = r} z[node_s] * acc[s]   (relation-major reduction; every pair
 //                                                                 was visited from both ends).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -493,10 +495,22 @@ int tipb_edges_mirrored(const int64_t* edge_index, const int64_t* range_list, in
     return TIPB_OK;
 }
 
+int tipb_decoder_sweep_status(void) {
+    int flag = 0;
+    if (cudaMemcpy(&flag, sweep_tc_error_flag(), sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (flag) cudaMemset(sweep_tc_error_flag(), 0, sizeof(int));
+    return flag;
+}
+
 int tipb_decoder_sweep(const float* z, const float* weight, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid,
                        float* out, void* stream) {
     TIPB_CHECK_ARG(z && weight && out, "decoder_sweep: NULL argument");
     TIPB_CHECK_ARG(dim >= 1 && dim <= 1024 && n_rel <= 65535, "decoder_sweep: dim/n_rel out of range");
+    // tcgen05 path (sweep_tc.cu): the contraction as one bf16x3-split GEMM with TMEM accumulators, write-bound
+    static const bool tc_off = getenv("TIPB_SWEEP_TC") && getenv("TIPB_SWEEP_TC")[0] == '0';
+    if (!tc_off && sweep_tc_supported(n_nodes, n_rel, dim) && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(weight) & 15) == 0)
+        return sweep_tc_run(z, weight, n_nodes, n_rel, dim, apply_sigmoid, out, (cudaStream_t)stream);
     const bool tiled_ok = (dim == 4 || dim == 8 || dim == 16 || dim == 32) && n_nodes < (int64_t(1) << 24) &&
                           (size_t(n_nodes) * (dim / 4 + 1) + size_t(SWEEP_ROWS) * (dim / 4)) * sizeof(float4) + 1024 <=
                               size_t(max_smem_optin()) &&

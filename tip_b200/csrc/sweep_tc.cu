@@ -1,0 +1,342 @@
+// Decoder sweep on the 5th-generation tensor cores (BASELINE.json config 5: all N x N drug pairs x R relations;
+// reference: MultiInnerProductDecoder.forward evaluated on every pair, src/layers.py:590-592).
+//
+//   out[r, i, j] = act( sum_k z[i,k] w[r,k] z[j,k] )            1.43 GB of fp32 scores at 645 x 645 x 861
+//
+// The CUDA-core kernel (decoder.cu: k_decoder_sweep_tiled) is bound by 11.5 GFLOP of fp32 FMA plus the sigmoid
+// (23 % of the HBM write roofline).  Here the contraction runs as ONE GEMM on tcgen05:
+//
+//   D[j, c] = sum_kk A'[j, kk] B'[c, kk],      c = r * N + i  (555,345 rows),   kk = 0 .. 6 * dim
+//
+// fp32 accuracy from bf16 operands: x = hi + mid + lo (three bf16 pieces, 24 significant bits) and the six products
+// hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi are laid side by side along K (the dropped terms are <= 2^-24
+// relative); A' holds the pieces of z[j], B' those of u = z[i] * w[r].  Accumulation is fp32 in TMEM.
+//
+// One persistent CTA per SM.  A' (all of z, 6 M-tiles of 128 rows) is built once; per N-tile of 256 rows c:
+//   builder warps   compute u, split it, store B' in the canonical K-major no-swizzle UMMA layout, fence, arrive
+//   MMA thread      per M-tile: wait for a free TMEM accumulator (2 x 256 columns), issue 6*dim/16 tcgen05.mma
+//                   (M 128, N 256, K 16), commit to the "full" mbarrier
+//   epilogue warps  tcgen05.ld 32 columns at a time, sigmoid (ex2 + rcp), and store: TMEM lane = j, so for a fixed
+//                   column the 32 lanes of a warp write 32 consecutive floats of out[r, i, :] -- coalesced although
+//                   the row pitch (645 floats) allows neither 128-bit nor TMA stores
+// The output stream (1.43 GB) is the roofline; MMA time is ~2 us of the ~15 us a tile's stores need.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace tipb {
+
+constexpr int ST_THREADS = 256;          // warps 0-3: epilogue, warp 4: MMA issue, warps 5-7: B' builders
+constexpr int ST_EPI_WARPS = 4;
+constexpr int ST_BUILD_THREADS = ST_THREADS - 32 * (ST_EPI_WARPS + 1);
+constexpr int ST_TILE_N = 256;           // rows c per N-tile = MMA N = TMEM columns per accumulator
+constexpr int ST_TILE_M = 128;           // rows j per M-tile = MMA M = TMEM lanes
+constexpr int ST_MAX_MTILES = 6;         // n_nodes <= 768
+constexpr uint32_t ST_SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug becomes an error flag, not a hang
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < ST_SPIN_LIMIT; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> f32, one K = 16 step
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 bytes
+// stored contiguously (128 B); LBO = byte distance between the two core matrices of one K = 16 step, SBO = byte
+// distance between 8-row groups; version 1 (sm_100), layout type 0 (no swizzle)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3fffu);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= uint64_t(1) << 46;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
+// N >> 3 at bits [17,23), M >> 4 at bits [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// the three bf16 pieces of 8 consecutive floats -> three 16-byte chunks (8 bf16 each)
+struct Pieces8 { uint4 hi, mid, lo; };
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ Pieces8 split8(const float (&x)[8]) {
+    float h[8], m[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+        const float r1 = x[i] - h[i];                     // exact
+        m[i] = __bfloat162float(__float2bfloat16_rn(r1));
+        l[i] = r1 - m[i];                                 // exact; rounded to bf16 when packed
+    }
+    Pieces8 p;
+    p.hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    p.mid = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    p.lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    return p;
+}
+
+// operand row layout: K = 6 * DIM bf16 per row = 12 * DIM bytes; an 8-row group = (6 * DIM / 8) core matrices
+template <int DIM>
+struct SweepLayout {
+    static constexpr int K = 6 * DIM;                 // bf16 elements per row
+    static constexpr int KSTEPS = K / 16;
+    static constexpr int CHUNKS = K / 8;              // 16-byte chunks per row
+    static constexpr int LBO = 128;                   // adjacent core matrices along K
+    static constexpr int SBO = CHUNKS * 128;          // next 8-row group
+    static constexpr int A_TILE_BYTES = (ST_TILE_M / 8) * SBO;
+    static constexpr int B_TILE_BYTES = (ST_TILE_N / 8) * SBO;
+    __device__ static uint32_t chunk_offset(int row, int chunk) { return uint32_t((row >> 3) * SBO + chunk * 128 + (row & 7) * 16); }
+};
+
+// slice s of the K axis (DIM elements each) carries which piece of A (z[j]) and of B (u): products
+// hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
+__device__ __forceinline__ uint4 piece_a(const Pieces8& p, int s) { return (s == 2 || s == 3) ? p.mid : (s == 5 ? p.lo : p.hi); }
+__device__ __forceinline__ uint4 piece_b(const Pieces8& p, int s) { return (s == 1 || s == 3) ? p.mid : (s == 4 ? p.lo : p.hi); }
+
+template <int DIM>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int n_nodes, int n_rel, int apply_sigmoid,
+                   float* __restrict__ out, int* __restrict__ error_flag) {
+    using LY = SweepLayout<DIM>;
+    extern __shared__ __align__(1024) uint8_t st_smem[];
+    const int m_tiles = (n_nodes + ST_TILE_M - 1) / ST_TILE_M;
+    uint8_t* sA = st_smem;                                           // [m_tiles] A' tiles
+    uint8_t* sB = sA + size_t(m_tiles) * LY::A_TILE_BYTES;            // one B' tile
+    __shared__ uint64_t bar_full[2], bar_empty[2], bar_b_ready, bar_b_free;
+    __shared__ uint32_t s_tmem_base;
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int64_t n_rows = int64_t(n_rel) * n_nodes;                 // rows c of B'
+    const int n_tiles = int((n_rows + ST_TILE_N - 1) / ST_TILE_N);
+
+    // ---- setup: barriers, TMEM, A'
+    if (tid == 0) {
+        mbar_init(&bar_full[0], 1);
+        mbar_init(&bar_full[1], 1);
+        mbar_init(&bar_empty[0], 32 * ST_EPI_WARPS);
+        mbar_init(&bar_empty[1], 32 * ST_EPI_WARPS);
+        mbar_init(&bar_b_ready, ST_BUILD_THREADS);
+        mbar_init(&bar_b_free, 1);
+        fence_barrier_init();
+    }
+    if (wid == ST_EPI_WARPS) tmem_alloc(&s_tmem_base, 512);
+    // A'[j, slice s, k] = piece_a(z[j, k]); rows j >= n_nodes are zero
+    for (int idx = tid; idx < m_tiles * ST_TILE_M * (DIM / 8); idx += ST_THREADS) {
+        const int j = idx / (DIM / 8), c8 = idx % (DIM / 8);
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = j < n_nodes ? z[size_t(j) * DIM + c8 * 8 + i] : 0.f;
+        const Pieces8 p = split8(x);
+        uint8_t* tile = sA + size_t(j / ST_TILE_M) * LY::A_TILE_BYTES;
+        const int row = j % ST_TILE_M;
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+            *reinterpret_cast<uint4*>(tile + LY::chunk_offset(row, s * (DIM / 8) + c8)) = piece_a(p, s);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (wid < ST_EPI_WARPS) {
+        // =========================================================== epilogue: TMEM -> sigmoid -> global
+        uint32_t it = 0;
+        bool ok = true;
+        for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x) {
+            const int64_t c0 = int64_t(t) * ST_TILE_N;
+            for (int m = 0; m < m_tiles && ok; ++m, ++it) {
+                const uint32_t b = it & 1u;
+                ok = mbar_wait(&bar_full[b], (it >> 1) & 1u);
+                if (!ok) break;
+                tc_fence_after();
+                const int j = m * ST_TILE_M + wid * 32 + lane;
+                const bool j_ok = j < n_nodes;
+#pragma unroll 1
+                for (int ch = 0; ch < ST_TILE_N / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (uint32_t(wid * 32) << 16) + b * ST_TILE_N + ch * 32, v);
+                    const int64_t c = c0 + ch * 32;
+                    float* dst = out + c * n_nodes + j;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        float val = __uint_as_float(v[q]);
+                        if (apply_sigmoid) val = __frcp_rn(1.0f + __expf(-val));
+                        if (j_ok && c + q < n_rows) __stcs(dst + size_t(q) * n_nodes, val);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_empty[b]);
+            }
+        }
+        if (!ok) atomicExch(error_flag, 1);
+    } else if (wid == ST_EPI_WARPS) {
+        // =========================================================== MMA issue (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(ST_TILE_M, ST_TILE_N);
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            uint32_t it = 0, tile_no = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++tile_no) {
+                ok = mbar_wait(&bar_b_ready, tile_no & 1u);
+                if (!ok) break;
+                tc_fence_after();
+                for (int m = 0; m < m_tiles && ok; ++m, ++it) {
+                    const uint32_t b = it & 1u;
+                    ok = mbar_wait(&bar_empty[b], ((it >> 1) & 1u) ^ 1u);    // passes at once the first two times
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + b * ST_TILE_N;
+#pragma unroll
+                    for (int ks = 0; ks < LY::KSTEPS; ++ks) {
+                        const uint64_t da = umma_desc(a_base + m * LY::A_TILE_BYTES + ks * 2 * LY::LBO, LY::LBO, LY::SBO);
+                        const uint64_t db = umma_desc(b_base + ks * 2 * LY::LBO, LY::LBO, LY::SBO);
+                        umma_bf16(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&bar_full[b]);          // arrives when these MMAs have written the accumulator
+                }
+                umma_commit(&bar_b_free);               // ... and when every MMA that read this B' tile is done
+            }
+            if (!ok) atomicExch(error_flag, 2);
+        }
+    } else {
+        // =========================================================== B' builders
+        const int bt = tid - 32 * (ST_EPI_WARPS + 1);
+        uint32_t tile_no = 0;
+        bool ok = true;
+        for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++tile_no) {
+            if (tile_no > 0) {
+                ok = mbar_wait(&bar_b_free, (tile_no - 1) & 1u);
+                if (!ok) break;
+            }
+            const int64_t c0 = int64_t(t) * ST_TILE_N;
+            for (int idx = bt; idx < ST_TILE_N * (DIM / 8); idx += ST_BUILD_THREADS) {
+                const int row = idx / (DIM / 8), c8 = idx % (DIM / 8);
+                const int64_t c = c0 + row;
+                float x[8];
+                if (c < n_rows) {
+                    const int r = int(c / n_nodes), i = int(c - int64_t(r) * n_nodes);
+                    const float4 z0 = *reinterpret_cast<const float4*>(z + size_t(i) * DIM + c8 * 8);
+                    const float4 z1 = *reinterpret_cast<const float4*>(z + size_t(i) * DIM + c8 * 8 + 4);
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + size_t(r) * DIM + c8 * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + size_t(r) * DIM + c8 * 8 + 4);
+                    x[0] = z0.x * w0.x; x[1] = z0.y * w0.y; x[2] = z0.z * w0.z; x[3] = z0.w * w0.w;
+                    x[4] = z1.x * w1.x; x[5] = z1.y * w1.y; x[6] = z1.z * w1.z; x[7] = z1.w * w1.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = 0.f;
+                }
+                const Pieces8 p = split8(x);
+#pragma unroll
+                for (int s = 0; s < 6; ++s)
+                    *reinterpret_cast<uint4*>(sB + LY::chunk_offset(row, s * (DIM / 8) + c8)) = piece_b(p, s);
+            }
+            fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(&bar_b_ready);
+        }
+        if (!ok) atomicExch(error_flag, 3);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (wid == ST_EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int DIM>
+static int sweep_tc_launch(const float* z, const float* w, int64_t n_nodes, int64_t n_rel, int apply_sigmoid, float* out,
+                           int* error_flag, cudaStream_t s) {
+    using LY = SweepLayout<DIM>;
+    const int m_tiles = int(ceil_div(n_nodes, ST_TILE_M));
+    const size_t smem = size_t(m_tiles) * LY::A_TILE_BYTES + LY::B_TILE_BYTES + 1024;
+    auto kern = k_decoder_sweep_tc<DIM>;
+    if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+    const int64_t n_tiles = ceil_div(n_rel * n_nodes, ST_TILE_N);
+    const int grid = int(n_tiles < sm_count() ? n_tiles : sm_count());
+    kern<<<grid, ST_THREADS, smem, s>>>(z, w, (int)n_nodes, (int)n_rel, apply_sigmoid, out, error_flag);
+    TIPB_CHECK_LAUNCH("decoder_sweep_tc");
+    return TIPB_OK;
+}
+
+__device__ int g_sweep_tc_error = 0;      // set by a role whose bounded barrier wait timed out (never in a correct run)
+
+int* sweep_tc_error_flag() {
+    static int* ptr = nullptr;
+    if (!ptr) cudaGetSymbolAddress(reinterpret_cast<void**>(&ptr), g_sweep_tc_error);
+    return ptr;
+}
+
+// 1 if the tensor-core sweep handles this shape (the generic kernels of decoder.cu take the rest)
+bool sweep_tc_supported(int64_t n_nodes, int64_t n_rel, int dim) {
+    if (dim != 8 && dim != 16) return false;
+    if (n_nodes < 1 || n_nodes > int64_t(ST_MAX_MTILES) * ST_TILE_M || n_rel < 1) return false;
+    const size_t smem = size_t(ceil_div(n_nodes, ST_TILE_M)) * (ST_TILE_M / 8) * (6 * dim / 8) * 128 +
+                        size_t(ST_TILE_N / 8) * (6 * dim / 8) * 128 + 2048;
+    return smem <= size_t(max_smem_optin()) && n_rel * n_nodes < (int64_t(1) << 31);
+}
+
+int sweep_tc_run(const float* z, const float* w, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid, float* out,
+                 cudaStream_t s) {
+    int* error_flag = sweep_tc_error_flag();
+    if (dim == 8) return sweep_tc_launch<8>(z, w, n_nodes, n_rel, apply_sigmoid, out, error_flag, s);
+    return sweep_tc_launch<16>(z, w, n_nodes, n_rel, apply_sigmoid, out, error_flag, s);
+}
+
+}  // namespace tipb

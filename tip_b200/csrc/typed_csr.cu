@@ -674,8 +674,10 @@ static int grp_warps(int64_t n_nodes) {
 static bool use_grouped(const int64_t* edge_type, const int64_t* range_list, int64_t entries, int64_t n_nodes,
                         int64_t n_other, int64_t n_rel, int doubled) {
     // (a doubled plan lists every pair under both endpoints: one validity rule for both copies needs one id space)
+    // (large node counts -- 10^4 drugs -- have no fast in-CTA placement: per-tile scans over all nodes would dominate,
+    // the stable radix sort of the generic path is the better builder there)
     return range_list && !edge_type && entries > 0 && n_rel > 1 && n_rel <= 65535 && grp_warps(n_nodes) > 0 &&
-           (!doubled || n_nodes == n_other) &&
+           place_warps(n_nodes, n_other) > 0 && (!doubled || n_nodes == n_other) &&
            n_nodes * n_rel <= 4 * entries + (int64_t(1) << 20);
 }
 
