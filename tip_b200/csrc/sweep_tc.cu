@@ -12,26 +12,37 @@
 // hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi are laid side by side along K (the dropped terms are <= 2^-24
 // relative); A' holds the pieces of z[j], B' those of u = z[i] * w[r].  Accumulation is fp32 in TMEM.
 //
-// One persistent CTA per SM.  A' (all of z, 6 M-tiles of 128 rows) is built once; per N-tile of 256 rows c:
-//   builder warps   compute u, split it, store B' in the canonical K-major no-swizzle UMMA layout, fence, arrive
-//   MMA thread      per M-tile: wait for a free TMEM accumulator (2 x 256 columns), issue 6*dim/16 tcgen05.mma
-//                   (M 128, N 256, K 16), commit to the "full" mbarrier
-//   epilogue warps  tcgen05.ld 32 columns at a time, sigmoid (ex2 + rcp), and store: TMEM lane = j, so for a fixed
-//                   column the 32 lanes of a warp write 32 consecutive floats of out[r, i, :] -- coalesced although
-//                   the row pitch (645 floats) allows neither 128-bit nor TMA stores
-// The output stream (1.43 GB) is the roofline; MMA time is ~2 us of the ~15 us a tile's stores need.
+// One persistent CTA per SM (640 threads).  A' (the pieces of all of z, 6 M-tiles of 128 rows) is built once; per
+// N-tile of 256 rows c:
+//   builder warps   compute u, split it, store B' (double buffered) in the canonical K-major no-swizzle UMMA layout,
+//                   fence.proxy.async, arrive
+//   MMA thread      per M-tile: wait for a free TMEM accumulator (2 x 256 columns), issue the six piece products as
+//                   tcgen05.mma (M 128, N 256, K 16) selecting the pieces through the descriptor start addresses,
+//                   tcgen05.commit to the "full" mbarrier
+//   epilogue warps  (16: four per TMEM lane quarter) request both of their 32-column chunks from TMEM before waiting
+//                   (one tcgen05.ld at a time reads TMEM at 30 B/clk/SM, two in flight on 16 warps at > 120), apply
+//                   the sigmoid (ex2 + rcp), stage the chunk in shared memory and write it as LINE-ALIGNED stores: the
+//                   output is one flat array whose rows (645 floats) start at arbitrary 4-byte offsets, and warp
+//                   stores that straddle lines run at ~60 % of the rate of whole lines (measured: 323 vs 500 us)
+// Every barrier wait is bounded (a protocol fault sets a flag, tipb_decoder_sweep_status, instead of hanging the GPU).
+// Measured on B200 (tools/ubench_sweep.py, profiles/): 415 us = 3.45 TB/s written = 53 % of the measured copy peak, from
+// 931 us for the CUDA-core kernel; MMAs + handshakes alone 59 us, + TMEM loads 69 us, + sigmoid and staging 242 us:
+// the rest is the store loop (two partial lines per 512-byte row segment).  Bits 1..6 of `apply_sigmoid` switch parts of
+// the epilogue off -- they exist for exactly these measurements and are not part of the ABI contract.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace tipb {
 
-constexpr int ST_THREADS = 256;          // warps 0-3: epilogue, warp 4: MMA issue, warps 5-7: B' builders
-constexpr int ST_EPI_WARPS = 4;
+constexpr int ST_THREADS = 640;          // warps 0-15: epilogue, warp 16: MMA issue, warps 17-19: B' builders
+constexpr int ST_EPI_WARPS = 16;         // warp w drains TMEM lanes 32 (w % 4) .. + 32; the four warps w / 4 = g form group g
+constexpr int ST_GROUPS = ST_EPI_WARPS / 4;
 constexpr int ST_BUILD_THREADS = ST_THREADS - 32 * (ST_EPI_WARPS + 1);
 constexpr int ST_TILE_N = 256;           // rows c per N-tile = MMA N = TMEM columns per accumulator
 constexpr int ST_TILE_M = 128;           // rows j per M-tile = MMA M = TMEM lanes
 constexpr int ST_MAX_MTILES = 6;         // n_nodes <= 768
+constexpr int ST_CH_PER_WARP = ST_TILE_N / 32 / ST_GROUPS;     // 32-column chunks of an accumulator per warp: 2
 constexpr uint32_t ST_SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug becomes an error flag, not a hang
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -88,8 +99,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 bytes
 // stored contiguously (128 B); LBO = byte distance between the two core matrices of one K = 16 step, SBO = byte
@@ -130,23 +141,25 @@ __device__ __forceinline__ Pieces8 split8(const float (&x)[8]) {
     return p;
 }
 
-// operand row layout: K = 6 * DIM bf16 per row = 12 * DIM bytes; an 8-row group = (6 * DIM / 8) core matrices
+// operand row layout: the three bf16 pieces [hi | mid | lo] of a row side by side, DIM = 16 elements (one K = 16 MMA
+// step) each; the six products pick their pieces through the descriptor start address
 template <int DIM>
 struct SweepLayout {
-    static constexpr int K = 6 * DIM;                 // bf16 elements per row
-    static constexpr int KSTEPS = K / 16;
-    static constexpr int CHUNKS = K / 8;              // 16-byte chunks per row
+    static_assert(DIM == 16, "one piece = one K = 16 step");
+    static constexpr int K = 3 * DIM;                 // bf16 elements per row
+    static constexpr int CHUNKS = K / 8;              // 16-byte chunks per row (6)
     static constexpr int LBO = 128;                   // adjacent core matrices along K
     static constexpr int SBO = CHUNKS * 128;          // next 8-row group
+    static constexpr int PIECE_BYTES = 2 * LBO;       // one piece = two core matrices along K
     static constexpr int A_TILE_BYTES = (ST_TILE_M / 8) * SBO;
     static constexpr int B_TILE_BYTES = (ST_TILE_N / 8) * SBO;
     __device__ static uint32_t chunk_offset(int row, int chunk) { return uint32_t((row >> 3) * SBO + chunk * 128 + (row & 7) * 16); }
 };
+// products hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi (piece index 0 = hi, 1 = mid, 2 = lo)
+__device__ __constant__ int c_piece_a[6] = {0, 0, 1, 1, 0, 2};
+__device__ __constant__ int c_piece_b[6] = {0, 1, 0, 1, 2, 0};
 
-// slice s of the K axis (DIM elements each) carries which piece of A (z[j]) and of B (u): products
-// hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
-__device__ __forceinline__ uint4 piece_a(const Pieces8& p, int s) { return (s == 2 || s == 3) ? p.mid : (s == 5 ? p.lo : p.hi); }
-__device__ __forceinline__ uint4 piece_b(const Pieces8& p, int s) { return (s == 1 || s == 3) ? p.mid : (s == 4 ? p.lo : p.hi); }
+constexpr int ST_STAGE_ROWS = 32, ST_STAGE_PITCH = ST_TILE_M + 4;      // staging of one 32-column chunk: [32 c][128 j]
 
 template <int DIM>
 __global__ void __launch_bounds__(ST_THREADS, 1)
@@ -156,8 +169,9 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
     extern __shared__ __align__(1024) uint8_t st_smem[];
     const int m_tiles = (n_nodes + ST_TILE_M - 1) / ST_TILE_M;
     uint8_t* sA = st_smem;                                           // [m_tiles] A' tiles
-    uint8_t* sB = sA + size_t(m_tiles) * LY::A_TILE_BYTES;            // one B' tile
-    __shared__ uint64_t bar_full[2], bar_empty[2], bar_b_ready, bar_b_free;
+    uint8_t* sB = sA + size_t(m_tiles) * LY::A_TILE_BYTES;            // two B' tiles (double buffered)
+    float* sStage = reinterpret_cast<float*>(sB + 2 * LY::B_TILE_BYTES);   // [groups][32][PITCH] epilogue staging
+    __shared__ uint64_t bar_full[2], bar_empty[2], bar_b_ready[2], bar_b_free[2];
     __shared__ uint32_t s_tmem_base;
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -166,16 +180,16 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
 
     // ---- setup: barriers, TMEM, A'
     if (tid == 0) {
-        mbar_init(&bar_full[0], 1);
-        mbar_init(&bar_full[1], 1);
-        mbar_init(&bar_empty[0], 32 * ST_EPI_WARPS);
-        mbar_init(&bar_empty[1], 32 * ST_EPI_WARPS);
-        mbar_init(&bar_b_ready, ST_BUILD_THREADS);
-        mbar_init(&bar_b_free, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar_full[b], 1);
+            mbar_init(&bar_empty[b], ST_EPI_WARPS);
+            mbar_init(&bar_b_ready[b], ST_BUILD_THREADS);
+            mbar_init(&bar_b_free[b], 1);
+        }
         fence_barrier_init();
     }
     if (wid == ST_EPI_WARPS) tmem_alloc(&s_tmem_base, 512);
-    // A'[j, slice s, k] = piece_a(z[j, k]); rows j >= n_nodes are zero
+    // A'[j, piece, k]; rows j >= n_nodes are zero
     for (int idx = tid; idx < m_tiles * ST_TILE_M * (DIM / 8); idx += ST_THREADS) {
         const int j = idx / (DIM / 8), c8 = idx % (DIM / 8);
         float x[8];
@@ -184,9 +198,9 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
         const Pieces8 p = split8(x);
         uint8_t* tile = sA + size_t(j / ST_TILE_M) * LY::A_TILE_BYTES;
         const int row = j % ST_TILE_M;
-#pragma unroll
-        for (int s = 0; s < 6; ++s)
-            *reinterpret_cast<uint4*>(tile + LY::chunk_offset(row, s * (DIM / 8) + c8)) = piece_a(p, s);
+        *reinterpret_cast<uint4*>(tile + LY::chunk_offset(row, 0 * (DIM / 8) + c8)) = p.hi;
+        *reinterpret_cast<uint4*>(tile + LY::chunk_offset(row, 1 * (DIM / 8) + c8)) = p.mid;
+        *reinterpret_cast<uint4*>(tile + LY::chunk_offset(row, 2 * (DIM / 8) + c8)) = p.lo;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -195,7 +209,15 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
     const uint32_t tmem_base = s_tmem_base;
 
     if (wid < ST_EPI_WARPS) {
-        // =========================================================== epilogue: TMEM -> sigmoid -> global
+        // =========================================================== epilogue: TMEM -> sigmoid -> staging -> global
+        // The output is one flat array (row c of B' = 645 consecutive floats): a warp store of 32 consecutive floats
+        // starts at an arbitrary 4-byte offset, and L2 handles the two partial sectors of every such store at about
+        // half the rate of whole lines.  So the four warps of a group (one per TMEM lane quarter) stage their
+        // [32 c][128 j] chunk in shared memory, and every warp then writes 8 of the rows as LINE-ALIGNED stores: lane l
+        // takes element 32 k + l - a of the row segment, a = the segment's offset inside its 128-byte line.
+        const int quarter = wid & 3, group = wid >> 2;
+        float* stage = sStage + size_t(group) * ST_STAGE_ROWS * ST_STAGE_PITCH;
+        const int bar_id = 1 + group;                                 // named barrier of the group's four warps
         uint32_t it = 0;
         bool ok = true;
         for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x) {
@@ -205,23 +227,61 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
                 ok = mbar_wait(&bar_full[b], (it >> 1) & 1u);
                 if (!ok) break;
                 tc_fence_after();
-                const int j = m * ST_TILE_M + wid * 32 + lane;
-                const bool j_ok = j < n_nodes;
-#pragma unroll 1
-                for (int ch = 0; ch < ST_TILE_N / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + (uint32_t(wid * 32) << 16) + b * ST_TILE_N + ch * 32, v);
-                    const int64_t c = c0 + ch * 32;
-                    float* dst = out + c * n_nodes + j;
+                const int seg_len = min(ST_TILE_M, n_nodes - m * ST_TILE_M);     // valid j of this M-tile
+                const bool have_lanes = quarter * 32 < seg_len;                  // (the last M-tile is mostly padding)
+                // both chunks of this warp are requested from TMEM before the first one is waited for
+                uint32_t v[ST_CH_PER_WARP][32];
+                if (have_lanes && !(apply_sigmoid & 32)) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        float val = __uint_as_float(v[q]);
-                        if (apply_sigmoid) val = __frcp_rn(1.0f + __expf(-val));
-                        if (j_ok && c + q < n_rows) __stcs(dst + size_t(q) * n_nodes, val);
+                    for (int u = 0; u < ST_CH_PER_WARP; ++u)
+                        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + b * ST_TILE_N + (group + u * ST_GROUPS) * 32, v[u]);
+                    tmem_ld_wait();
+                }
+#pragma unroll
+                for (int u = 0; u < ST_CH_PER_WARP; ++u) {
+                    const int ch = group + u * ST_GROUPS;
+                    if (apply_sigmoid & 16) {                      // (measurement aid: no staging, no stores)
+                        if (have_lanes && (v[u][0] ^ v[u][17]) == 0x12345678u) out[0] = 0.f;
+                        continue;
                     }
+                    if (have_lanes) {
+                        if (apply_sigmoid & 1) {                   // 1 / (1 + 2^(-v log2 e)): two SFU operations per score
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                float e, r;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(v[u][q]) * -1.4426950408889634f));
+                                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+                                v[u][q] = __float_as_uint(r);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) stage[q * ST_STAGE_PITCH + quarter * 32 + lane] = __uint_as_float(v[u][q]);
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (!(apply_sigmoid & 8)) {
+                        // rows quarter*8 .. +8 of the chunk; per row one per-thread pointer, the five line stores use
+                        // immediate offsets from it
+                        const int64_t c_first = c0 + ch * 32 + quarter * 8;
+                        int64_t f = c_first * n_nodes + m * ST_TILE_M;           // flat index of the row segment's first score
+                        const int rows = int(min(int64_t(8), n_rows - c_first));
+#pragma unroll 1
+                        for (int rr = 0; rr < rows; ++rr, f += n_nodes) {
+                            const int a = int(f & 31);
+                            float* __restrict__ p = out + (f - a) + lane;       // element `lane` of the segment's first line
+                            const float* __restrict__ src = stage + (quarter * 8 + rr) * ST_STAGE_PITCH - a + lane;
+                            const unsigned e0 = unsigned(lane - a);             // index inside the segment (wraps below 0)
+#pragma unroll
+                            for (int k = 0; k < ST_TILE_M / 32 + 1; ++k) {
+                                if ((apply_sigmoid & 64) && (k == 0 || k == ST_TILE_M / 32)) continue;   // (aid: whole lines only)
+                                if (e0 + unsigned(k * 32) < unsigned(seg_len)) p[k * 32] = src[k * 32];
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // staging is reused by the next chunk
                 }
                 tc_fence_before();
-                mbar_arrive(&bar_empty[b]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[b]);      // one arrival per epilogue warp
             }
         }
         if (!ok) atomicExch(error_flag, 1);
@@ -233,7 +293,8 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
             uint32_t it = 0, tile_no = 0;
             bool ok = true;
             for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++tile_no) {
-                ok = mbar_wait(&bar_b_ready, tile_no & 1u);
+                const uint32_t sb = tile_no & 1u;
+                ok = mbar_wait(&bar_b_ready[sb], (tile_no >> 1) & 1u);
                 if (!ok) break;
                 tc_fence_after();
                 for (int m = 0; m < m_tiles && ok; ++m, ++it) {
@@ -243,34 +304,36 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + b * ST_TILE_N;
 #pragma unroll
-                    for (int ks = 0; ks < LY::KSTEPS; ++ks) {
-                        const uint64_t da = umma_desc(a_base + m * LY::A_TILE_BYTES + ks * 2 * LY::LBO, LY::LBO, LY::SBO);
-                        const uint64_t db = umma_desc(b_base + ks * 2 * LY::LBO, LY::LBO, LY::SBO);
-                        umma_bf16(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                    for (int p = 0; p < 6; ++p) {
+                        const uint64_t da = umma_desc(a_base + m * LY::A_TILE_BYTES + c_piece_a[p] * LY::PIECE_BYTES, LY::LBO, LY::SBO);
+                        const uint64_t db = umma_desc(b_base + sb * LY::B_TILE_BYTES + c_piece_b[p] * LY::PIECE_BYTES, LY::LBO, LY::SBO);
+                        umma_bf16(d_tmem, da, db, idesc, p > 0 ? 1u : 0u);
                     }
                     umma_commit(&bar_full[b]);          // arrives when these MMAs have written the accumulator
                 }
-                umma_commit(&bar_b_free);               // ... and when every MMA that read this B' tile is done
+                umma_commit(&bar_b_free[sb]);           // ... and when every MMA that read this B' tile is done
             }
             if (!ok) atomicExch(error_flag, 2);
         }
     } else {
-        // =========================================================== B' builders
+        // =========================================================== B' builders (two tiles ahead of the epilogue)
         const int bt = tid - 32 * (ST_EPI_WARPS + 1);
         uint32_t tile_no = 0;
         bool ok = true;
         for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++tile_no) {
-            if (tile_no > 0) {
-                ok = mbar_wait(&bar_b_free, (tile_no - 1) & 1u);
+            const uint32_t sb = tile_no & 1u;
+            if (tile_no >= 2) {
+                ok = mbar_wait(&bar_b_free[sb], ((tile_no >> 1) - 1) & 1u);
                 if (!ok) break;
             }
+            uint8_t* tileB = sB + size_t(sb) * LY::B_TILE_BYTES;
             const int64_t c0 = int64_t(t) * ST_TILE_N;
             for (int idx = bt; idx < ST_TILE_N * (DIM / 8); idx += ST_BUILD_THREADS) {
                 const int row = idx / (DIM / 8), c8 = idx % (DIM / 8);
                 const int64_t c = c0 + row;
                 float x[8];
                 if (c < n_rows) {
-                    const int r = int(c / n_nodes), i = int(c - int64_t(r) * n_nodes);
+                    const int r = int(uint32_t(c) / uint32_t(n_nodes)), i = int(uint32_t(c) - uint32_t(r) * uint32_t(n_nodes));
                     const float4 z0 = *reinterpret_cast<const float4*>(z + size_t(i) * DIM + c8 * 8);
                     const float4 z1 = *reinterpret_cast<const float4*>(z + size_t(i) * DIM + c8 * 8 + 4);
                     const float4 w0 = *reinterpret_cast<const float4*>(w + size_t(r) * DIM + c8 * 8);
@@ -282,12 +345,12 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
                     for (int q = 0; q < 8; ++q) x[q] = 0.f;
                 }
                 const Pieces8 p = split8(x);
-#pragma unroll
-                for (int s = 0; s < 6; ++s)
-                    *reinterpret_cast<uint4*>(sB + LY::chunk_offset(row, s * (DIM / 8) + c8)) = piece_b(p, s);
+                *reinterpret_cast<uint4*>(tileB + LY::chunk_offset(row, 0 * (DIM / 8) + c8)) = p.hi;
+                *reinterpret_cast<uint4*>(tileB + LY::chunk_offset(row, 1 * (DIM / 8) + c8)) = p.mid;
+                *reinterpret_cast<uint4*>(tileB + LY::chunk_offset(row, 2 * (DIM / 8) + c8)) = p.lo;
             }
             fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(&bar_b_ready);
+            mbar_arrive(&bar_b_ready[sb]);
         }
         if (!ok) atomicExch(error_flag, 3);
     }
@@ -300,12 +363,16 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
     }
 }
 
+static size_t sweep_tc_smem(int64_t n_nodes, int dim) {
+    const size_t sbo = size_t(3 * dim / 8) * 128;
+    return size_t(ceil_div(n_nodes, ST_TILE_M)) * (ST_TILE_M / 8) * sbo + 2 * size_t(ST_TILE_N / 8) * sbo +
+           size_t(ST_EPI_WARPS / 4) * ST_STAGE_ROWS * ST_STAGE_PITCH * sizeof(float) + 1024;
+}
+
 template <int DIM>
 static int sweep_tc_launch(const float* z, const float* w, int64_t n_nodes, int64_t n_rel, int apply_sigmoid, float* out,
                            int* error_flag, cudaStream_t s) {
-    using LY = SweepLayout<DIM>;
-    const int m_tiles = int(ceil_div(n_nodes, ST_TILE_M));
-    const size_t smem = size_t(m_tiles) * LY::A_TILE_BYTES + LY::B_TILE_BYTES + 1024;
+    const size_t smem = sweep_tc_smem(n_nodes, DIM);
     auto kern = k_decoder_sweep_tc<DIM>;
     if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
     const int64_t n_tiles = ceil_div(n_rel * n_nodes, ST_TILE_N);
@@ -323,20 +390,17 @@ int* sweep_tc_error_flag() {
     return ptr;
 }
 
-// 1 if the tensor-core sweep handles this shape (the generic kernels of decoder.cu take the rest)
+// 1 if the tensor-core sweep handles this shape (the kernels of decoder.cu take the rest)
 bool sweep_tc_supported(int64_t n_nodes, int64_t n_rel, int dim) {
-    if (dim != 8 && dim != 16) return false;
+    if (dim != 16) return false;
     if (n_nodes < 1 || n_nodes > int64_t(ST_MAX_MTILES) * ST_TILE_M || n_rel < 1) return false;
-    const size_t smem = size_t(ceil_div(n_nodes, ST_TILE_M)) * (ST_TILE_M / 8) * (6 * dim / 8) * 128 +
-                        size_t(ST_TILE_N / 8) * (6 * dim / 8) * 128 + 2048;
-    return smem <= size_t(max_smem_optin()) && n_rel * n_nodes < (int64_t(1) << 31);
+    return sweep_tc_smem(n_nodes, dim) + 1024 <= size_t(max_smem_optin()) && n_rel * n_nodes < (int64_t(1) << 31);
 }
 
 int sweep_tc_run(const float* z, const float* w, int64_t n_nodes, int64_t n_rel, int dim, int apply_sigmoid, float* out,
                  cudaStream_t s) {
-    int* error_flag = sweep_tc_error_flag();
-    if (dim == 8) return sweep_tc_launch<8>(z, w, n_nodes, n_rel, apply_sigmoid, out, error_flag, s);
-    return sweep_tc_launch<16>(z, w, n_nodes, n_rel, apply_sigmoid, out, error_flag, s);
+    (void)dim;
+    return sweep_tc_launch<16>(z, w, n_nodes, n_rel, apply_sigmoid, out, sweep_tc_error_flag(), s);
 }
 
 }  // namespace tipb
