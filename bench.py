@@ -289,6 +289,9 @@ def roofline_block(model, serial_steps, step_s, peaks):
         fam_rows.append({"family": fam, "us": round(us, 1), "share": round(us / total_us, 4),
                          "algorithmic_bytes": int(a) if a else None,
                          "frac": round(a / (us * 1e-6) / 1e9 / peak, 3) if a else None})
+    kern_rows = [{"kernel": k, "us_per_step": round(v["us"] / n, 1), "launches_per_step": v["launches"] / n,
+                  "frac": round(v["alg"] / v["us"] * 1e6 / 1e9 / peak, 3) if v["alg"] else None}
+                 for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["us"])[:16]]
     step_alg = rf.step_algorithmic_bytes(W)
     block = {"bound": "hbm", "kernel": dom, "kernel_family": dk["family"], "kernel_share_of_step": round(dk["us"] / n / total_us, 4),
              "kernel_us": round(k_us, 2), "kernel_launches_per_step": launches,
@@ -301,7 +304,7 @@ def roofline_block(model, serial_steps, step_s, peaks):
              "serial_step_us": round(total_us, 1),
              "step": {"algorithmic_bytes": int(step_alg), "frac_of_timed_step": step_alg / step_s / 1e9 / peak,
                       "what": "SURVEY 8(d): sum of (A) over the step / the timed (overlapped, CUDA-graph) step time"},
-             "families": fam_rows,
+             "families": fam_rows, "kernels": kern_rows,
              "note": "(A) counts gathered payload rows, which this path serves from shared memory; where frac > 1 the "
                      "kernel is not HBM-bound (issue / shared-memory bound) and dram_frac is the DRAM-pin figure"}
     return block
@@ -343,10 +346,12 @@ def run_b200_arm(args):
         from tip_b200 import optim
         opt = optim.Adam(model.parameters(), lr=model.settings.lr)
 
+    one = torch.ones((), dtype=torch.float32, device=dev)     # d(loss)/d(loss): autograd would fill a fresh one per step
+
     def step():
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)
-        loss.backward()
+        loss.backward(one)
         opt.step()
         ns.join_prefetch(dev)        # the next step's MT19937 words were generated on a side stream meanwhile
         return model.last_loss if getattr(model, "defer_loss_reduce", False) else loss
@@ -458,6 +463,7 @@ def measure_e2e(model, opt, data, steps, e_total, world=1, sharded=False):
     import torch.distributed as dist
     dev = model.device
     d = model.data
+    one = torch.ones((), dtype=torch.float32, device=dev)
     pairs = []          # (device tensor, pinned host tensor)
     if sharded:
         pairs.append((model.local_idx, data["dd_train_idx"][:, model.e_lo:model.e_hi].contiguous().pin_memory()))
@@ -474,7 +480,7 @@ def measure_e2e(model, opt, data, steps, e_total, world=1, sharded=False):
             model.refresh_shard()
         opt.zero_grad(set_to_none=True)
         loss = model(check_status=False)
-        loss.backward()
+        loss.backward(one)
         opt.step()
         out = model.last_loss if getattr(model, "defer_loss_reduce", False) else loss
         return out.item()                     # device -> host

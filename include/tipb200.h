@@ -292,6 +292,76 @@ int tipb_adam_step(int n_tensors, void* const* params, const void* const* grads,
                    void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
                    float* step_dev, void* stream);
 
+/* ---------------------------------------------------------------- dense pieces + ablation operators
+ * Small fp32 products that the reference leaves to torch: GCNConv.lin (`self.lin(x)`, torch_geometric 2.0.1, called at
+ * src/layers.py:391-395), NNDecoder's two layers (src/layers.py:618-631), HierEncoder / FMEncoder's
+ * `torch.matmul(feat, embed)` (src/layers.py:541, 571).  Row-major, CUDA cores (every product is far below 1 GFLOP).
+ *   tipb_gemm       c[m,n] = a[m,k] * (trans_b ? b[n,k]^T : b[k,n]) (+ bias[n]) (+ ReLU)
+ *   tipb_gemm_tn    out[m,n] = a[k,m]^T * b[k,n]  (weight gradients; split-K summed in slice order: deterministic)
+ *   tipb_relu_grad_colsum   g = gy * (relu_out > 0) and d_bias[n] = sum_m g[m,n] (the ReLU mask and bias gradient of
+ *                   `F.relu(conv1(...))` / GCNConv.bias, src/layers.py:391-393); relu_out NULL: no mask, g not written
+ *   tipb_transpose  out[cols,rows] = in^T  (lin.weight^T of an identity feature matrix, prepare.py:22-23) */
+int tipb_gemm(const float* a, const float* b, const float* bias /* nullable */, int64_t m, int64_t n, int64_t k, int trans_b,
+              int relu, float* c, void* stream);
+size_t tipb_gemm_tn_workspace_bytes(int64_t m, int64_t n);
+int tipb_gemm_tn(const float* a, const float* b, int64_t k, int64_t m, int64_t n, float* out, void* ws, size_t ws_bytes,
+                 void* stream);
+size_t tipb_relu_grad_colsum_workspace_bytes(int64_t n);
+int tipb_relu_grad_colsum(const float* gy, const float* relu_out /* nullable */, int64_t m, int64_t n,
+                          float* g /* nullable iff relu_out is */, float* d_bias /* nullable */, void* ws, size_t ws_bytes,
+                          void* stream);
+int tipb_transpose(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
+/* FMEncoder.forward glue (src/layers.py:541-547): out[i] = cat(embed_out[i] / d_norm[i], hier_out[i]) (mode 0, 'cat')
+ * or embed_out[i] / d_norm[i] + hier_out[i] (mode 1, 'add'; f_embed == f_hier), and its gradient */
+int tipb_drug_input_fwd(const float* embed_out, const float* d_norm, const float* hier_out, int64_t n, int f_embed,
+                        int f_hier, int mode, float* out, void* stream);
+int tipb_drug_input_bwd(const float* grad, const float* d_norm, int64_t n, int f_embed, int f_hier, int mode,
+                        float* d_embed_out, float* d_hier_out, void* stream);
+/* out_a = a * *scalar_dev, out_b = b * *scalar_dev in one launch (the incoming loss gradient applied to the d_z / d_weight
+ * the fused loss kernels computed in their forward pass); tipb_fill_zero = cudaMemsetAsync (zero rows of a cat) */
+int tipb_scale2(const float* a, int64_t n_a, const float* b, int64_t n_b, const float* scalar_dev, float* out_a,
+                float* out_b, void* stream);
+int tipb_fill_zero(void* ptr, size_t bytes, void* stream);
+/* NNDecoder.forward (src/layers.py:618-631): sigmoid( relu(z_i W1) . w1_l2[r] + relu(z_j W2) . w2_l2[r] ).  The caller
+ * forms the per-node hidden layers and the tables table_a = relu(z W1) w1_l2^T, table_b = relu(z W2) w2_l2^T
+ * ([n_nodes, n_rel], tipb_gemm); the per-edge work is the gather of two scalars.  An out-of-range index gives NaN.
+ * Backward: d_table_a / d_table_b from the per-edge output gradient, as segment sums over typed CSRs of the scored edges
+ * grouped by (edge_index[0], relation) and by (edge_index[1], relation) -- no float atomics.  g_ws: n_edges floats. */
+int tipb_nn_decoder_fwd(const float* table_a, const float* table_b, const int64_t* edge_index, const int64_t* edge_type,
+                        int64_t n_edges, int64_t n_nodes, int64_t n_rel, int apply_sigmoid, float* out, void* stream);
+int tipb_nn_decoder_bwd(const void* plan_by_src, const void* plan_by_dst, int64_t n_edges, int64_t n_nodes, int64_t n_rel,
+                        const float* grad_out, const float* score, int apply_sigmoid, float* d_table_a, float* d_table_b,
+                        float* g_ws, void* stream);
+/* General sparse drug features (data/utils.py:117-132: identity + mono side-effect columns) as the front-end of
+ * `torch.matmul(x_drug, self.embed)` (src/layers.py:541): out[n_nodes, f] = S dense with S = COO entries
+ * (row, col, values[eid]) given as a typed CSR (n_rel = 1) over (col -> row) "edges"; the gradient wrt `dense` is the
+ * same call on the by-source plan (S^T). */
+int tipb_spmm_values(const void* plan, int64_t n_entries, int64_t n_nodes, const float* values, const float* dense, int f,
+                     float* out, void* stream);
+
+/* ---------------------------------------------------------------- train / test edge split
+ * process_edges (src/utils.py:35-65) and process_prot_edge (data/utils.py:212-229) on the device, bit-exact with the
+ * reference's use of the global numpy stream: per raw pair one np.random.binomial(1, p) draw = one 53-bit double =
+ * two MT19937 words; kept pairs followed by their mirror images per relation (src/utils.py:17-23), relation labels,
+ * cumulative ranges (src/utils.py:26-32); the dropped pairs form the test set the same way.
+ *   raw_index   int64 [2, n_raw]: the (row < col) pairs of all relations, concatenated in relation order
+ *   raw_ptr     int64 [n_rel + 1] (device): first pair of every relation, raw_ptr[n_rel] = n_raw
+ *   mt_state / stream_words / n_words   the numpy-compatible stream, as for tipb_neg_sample; needs 2 * n_raw unread words
+ *   qn = exp(log(1 - q)), px2 = (q * qn) / (1 - q) with q = min(p, 1 - p), formed by the caller in double exactly as
+ *        numpy's random_binomial_inversion forms them; invert = (p > 0.5)
+ *   tipb_edge_split_mask: kept_scan int32 [n_raw + 1] = exclusive scan of the keep flags (kept_scan[n_raw] = number of
+ *        train pairs); advances mt_state by 2 * n_raw words.  status: 0 ok, bit 1 = not enough words (state untouched),
+ *        bit 2 = a draw would have restarted numpy's inversion loop (U within 2^-53 of 1; state untouched)
+ *   tipb_edge_split_emit: train_idx int64 [2, 2K], train_et [2K], train_range [n_rel, 2], test_* likewise (K from the host
+ *        read of kept_scan[n_raw]: the one synchronisation of this data-preparation step) */
+size_t tipb_edge_split_workspace_bytes(int64_t n_raw);
+int tipb_edge_split_mask(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_words, int64_t n_raw, double qn,
+                         double px2, int invert, int32_t* kept_scan, int32_t* status, void* ws, size_t ws_bytes,
+                         void* stream);
+int tipb_edge_split_emit(const int64_t* raw_index, const int64_t* raw_ptr, int64_t n_raw, int64_t n_rel,
+                         const int32_t* kept_scan, int64_t n_train_pairs, int64_t* train_idx, int64_t* train_et,
+                         int64_t* train_range, int64_t* test_idx, int64_t* test_et, int64_t* test_range, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

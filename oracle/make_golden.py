@@ -200,12 +200,76 @@ def golden_layers(layers, ns, utils):
     np.savez_compressed(os.path.join(OUT, "layers.npz"), **flat)
 
 
+def golden_ablation(layers, utils):
+    """NNDecoder, HierEncoder (src/layers.py:556-637) and an FMEncoder fed with general sparse
+    drug features (identity + mono side-effect columns, data/utils.py:117-132), from the reference's own classes.
+    Written to its own file so that the other fixtures (and their RNG history) stay byte-identical."""
+    flat = {}
+    d = _small_data_dict(utils)
+    n_drug, n_prot, n_rel = d["n_drug"], d["n_prot"], d["n_dd_et"]
+    ei, et = d["dd_train_idx"], d["dd_train_et"]
+    for k in ("dd_train_idx", "dd_train_et", "dd_train_range", "pp_train_indices", "dp_edge_index", "d_norm"):
+        flat[f"data/{k}"] = d[k].numpy()
+    for k in ("n_drug", "n_prot", "n_dd_et"):
+        flat[f"data/{k}"] = np.array(d[k])
+    torch.manual_seed(2222)
+    gen = np.random.Generator(np.random.PCG64(5))
+
+    # ---- NNDecoder on a shuffled edge order
+    perm = torch.randperm(ei.shape[1])
+    dec = layers.NNDecoder(12, n_rel, l1_dim=16)
+    z = torch.randn(n_drug, 12, requires_grad=True)
+    sc = dec(z, ei[:, perm], et[perm])
+    gs = torch.randn_like(sc)
+    sc.backward(gs)
+    flat.update({"nn/perm": perm.numpy(), "nn/z": z.detach().numpy(), "nn/score": sc.detach().numpy(), "nn/gscore": gs.numpy(),
+                 "nn/dz": z.grad.numpy()})
+    for n, p in dec.named_parameters():
+        flat[f"nn/{n}"], flat[f"nn/d_{n}"] = p.detach().numpy(), p.grad.numpy()
+
+    # ---- HierEncoder as test/pd_net.py:26,124 feeds it: dense identity rows for the sources, zero rows for the targets
+    enc = layers.HierEncoder(n_prot, 32, 16, n_prot, n_drug)
+    feat = torch.cat([utils.dense_id(n_prot), torch.zeros(n_drug, n_prot)], dim=0)
+    x_norm = torch.from_numpy(gen.uniform(0.5, 2.0, n_prot + n_drug).astype(np.float32))
+    out = enc(feat, d["dp_edge_index"], d["dp_range_list"], x_norm)
+    go = torch.randn_like(out)
+    out.backward(go)
+    flat.update({"hier_enc/x_norm": x_norm.numpy(), "hier_enc/out": out.detach().numpy(), "hier_enc/gout": go.numpy()})
+    for n, p in enc.named_parameters():
+        flat[f"hier_enc/{n}"], flat[f"hier_enc/d_{n}"] = p.detach().numpy(), p.grad.numpy()
+
+    # ---- FMEncoder with sparse drug features [n_drug, n_drug + n_mono] and a non-trivial d_norm
+    n_mono = 30
+    mono_r = gen.integers(0, n_drug, 150)
+    mono_c = gen.integers(0, n_mono, 150)
+    pairs = np.unique(np.stack([mono_r, mono_c]), axis=1)
+    row = np.concatenate([np.arange(n_drug), pairs[0]])
+    col = np.concatenate([np.arange(n_drug), pairs[1] + n_drug])
+    d_feat = torch.sparse_coo_tensor(torch.from_numpy(np.stack([row, col])), torch.ones(len(row)), (n_drug, n_drug + n_mono))
+    d_norm = torch.sqrt(torch.sparse.sum(d_feat, dim=1).to_dense())
+    fm = layers.FMEncoder(torch.device("cpu"), n_drug + n_mono, n_rel, n_prot, n_prot, n_drug, prot_drug_dim=16,
+                          num_base=8, n_embed=48, n_hid1=32, n_hid2=16, mod="cat")
+    zz = fm(d_feat, ei, et, d["dd_train_range"], d_norm, d["p_feat"], d["pp_train_indices"], d["dp_edge_index"],
+            d["dp_range_list"])
+    gz = torch.randn_like(zz)
+    zz.backward(gz)
+    flat.update({"fm_mono/feat_index": np.stack([row, col]).astype(np.int64), "fm_mono/n_mono": np.array(n_mono),
+                 "fm_mono/d_norm": d_norm.numpy(), "fm_mono/z": zz.detach().numpy(), "fm_mono/gz": gz.numpy()})
+    for n, p in fm.named_parameters():
+        flat[f"fm_mono/param/{n}"], flat[f"fm_mono/grad/{n}"] = p.detach().numpy().copy(), p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ablation.npz"), **flat)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     layers, ns, utils = _import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "ablation":      # only the file added in round 2
+        golden_ablation(layers, utils)
+        return
     golden_neg_sampling(ns)
     golden_layout(utils)
     golden_layers(layers, ns, utils)
+    golden_ablation(layers, utils)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

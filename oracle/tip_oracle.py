@@ -157,6 +157,19 @@ def decoder(z, edge_index, edge_type, weight, sigmoid=True):
     return torch.sigmoid(value) if sigmoid else value
 
 
+def nn_decoder(z, edge_index, edge_type, w1_l1, w1_l2, w2_l1, w2_l2):
+    """NNDecoder.forward (src/layers.py:618-631): per-edge two-layer scorer of the DR-NN / PR-HMP-NN ablations."""
+    d1 = torch.relu(z[edge_index[0]] @ w1_l1)
+    d2 = torch.relu(z[edge_index[1]] @ w2_l1)
+    return torch.sigmoid((d1 * w1_l2[edge_type]).sum(dim=1) + (d2 * w2_l2[edge_type]).sum(dim=1))
+
+
+def hier_encoder(source_feat, edge_index, x_norm, embed, weight, n_source, n_target):
+    """HierEncoder.forward (src/layers.py:570-575): feat @ embed, / x_norm, hierarchy conv."""
+    x = (source_feat @ embed) / x_norm.view(-1, 1)
+    return hier_conv(x, edge_index, weight, n_source, n_target)
+
+
 def tip_loss(pos_score, neg_score):
     """TIP.forward loss (src/layers.py:338-340)."""
     return -torch.log(pos_score + EPS).mean() - torch.log(1 - neg_score + EPS).mean()
@@ -224,7 +237,9 @@ class TipOracle(object):
                           p["encoder.pp_encoder.conv2.bias"])
         x_prot = torch.cat((x_prot, torch.zeros((self.n_drug, x_prot.shape[1]), dtype=dtype)))
         x_pd = hier_conv(x_prot, d["dp_edge_index"], p["encoder.hgcn.weight"], self.n_prot, self.n_drug)
-        x_drug = p["encoder.embed"] / d["d_norm"].to(dtype).view(-1, 1)
+        # identity drug features: x @ embed == embed; general sparse features (data/utils.py:117-132) via "d_feat"
+        x_drug = p["encoder.embed"] if d.get("d_feat") is None else torch.sparse.mm(d["d_feat"].to(dtype), p["encoder.embed"])
+        x_drug = x_drug / d["d_norm"].to(dtype).view(-1, 1)
         x_drug = torch.cat((x_drug, x_pd), dim=1) if self.mod == "cat" else x_drug + x_pd
         ei, et, rl = d["dd_train_idx"], d["dd_train_et"], d["dd_train_range"]
         x_drug = torch.relu(self._rgcn("rgcn1", x_drug, ei, et, rl))

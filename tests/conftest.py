@@ -32,3 +32,8 @@ def golden_neg():
 @pytest.fixture(scope="session")
 def golden_layout():
     return load_golden("layout.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_ablation():
+    return load_golden("ablation.npz")

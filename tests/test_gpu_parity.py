@@ -255,6 +255,179 @@ def test_decoder_matches_reference(golden_layers):
     close(full, ref, what="dec sweep")
 
 
+# =============================================================================== ablation operators
+def test_dense_primitives_against_float64():
+    """tipb_gemm / tipb_gemm_tn / tipb_relu_grad_colsum / tipb_transpose through ops.matmul on ragged shapes"""
+    from tip_b200 import ops
+    d = dev()
+    rng = np.random.default_rng(3)
+    for (m, k, n, trans_b, bias, relu) in [(1, 1, 1, False, False, False), (645, 64, 32, False, True, True),
+                                           (19081 // 7, 32, 16, True, True, False), (70, 37, 53, True, False, True),
+                                           (130, 5, 861, True, True, True), (0, 8, 8, False, False, False)]:
+        x = torch.from_numpy(rng.standard_normal((m, k)).astype(np.float32)).to(d).requires_grad_(True)
+        w = torch.from_numpy(rng.standard_normal((n, k) if trans_b else (k, n)).astype(np.float32)).to(d).requires_grad_(True)
+        b = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(d).requires_grad_(True) if bias else None
+        y = ops.matmul(x, w, trans_b=trans_b, bias=b, relu=relu)
+        x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+        b64 = b.detach().double().requires_grad_(True) if bias else None
+        r = x64 @ (w64.t() if trans_b else w64)
+        if bias:
+            r = r + b64
+        if relu:
+            r = torch.relu(r)
+        close(y, r, what=f"matmul {m}x{k}x{n}")
+        if m == 0:
+            continue
+        g = torch.from_numpy(rng.standard_normal((m, n)).astype(np.float32)).to(d)
+        y.backward(g)
+        r.backward(g.double())
+        close(x.grad, x64.grad, what="matmul d_x")
+        close(w.grad, w64.grad, what="matmul d_w")
+        if bias:
+            close(b.grad, b64.grad, what="matmul d_bias")
+    t = torch.from_numpy(rng.standard_normal((77, 130)).astype(np.float32)).to(d).requires_grad_(True)
+    tt = ops.transpose2d(t)
+    assert tt.is_contiguous() and torch.equal(tt, t.detach().t())
+    tt.backward(torch.ones_like(tt) * 2)
+    assert t.grad.is_contiguous() and torch.equal(t.grad, torch.full_like(t, 2.0))
+
+
+def test_nn_decoder_matches_reference(golden_ablation):
+    from tip_b200 import layers
+    d, g = dev(), golden_ablation
+    n_rel = int(g["data/n_dd_et"])
+    perm = T(g["nn/perm"], d)
+    ei, et = T(g["data/dd_train_idx"], d)[:, perm].contiguous(), T(g["data/dd_train_et"], d)[perm].contiguous()
+    torch.manual_seed(1)
+    dec = layers.NNDecoder(12, n_rel, l1_dim=16).to(d)
+    assert [n for n, _ in dec.named_parameters()] == ["w1_l1", "w1_l2", "w2_l1", "w2_l2"]      # src/layers.py:606-613
+    with torch.no_grad():
+        for n, p in dec.named_parameters():
+            p.copy_(T(g["nn/" + n], d))
+    z = T(g["nn/z"], d).requires_grad_(True)
+    sc = dec(z, ei, et)
+    close(sc, g["nn/score"], what="nn score")
+    sc.backward(T(g["nn/gscore"], d))
+    close(z.grad, g["nn/dz"], what="nn dz")
+    for n, p in dec.named_parameters():
+        close(p.grad, g["nn/d_" + n], what="nn d_" + n)
+
+
+def test_hier_encoder_matches_reference(golden_ablation):
+    from tip_b200 import layers
+    d, g = dev(), golden_ablation
+    n_prot, n_drug = int(g["data/n_prot"]), int(g["data/n_drug"])
+    enc = layers.HierEncoder(n_prot, 32, 16, n_prot, n_drug).to(d)
+    assert [n for n, _ in enc.named_parameters()] == ["embed", "hgcn.weight"]
+    with torch.no_grad():
+        enc.embed.copy_(T(g["hier_enc/embed"], d))
+        enc.hgcn.weight.copy_(T(g["hier_enc/hgcn.weight"], d))
+    feat = torch.cat([torch.eye(n_prot), torch.zeros(n_drug, n_prot)]).to(d)          # test/pd_net.py:26
+    out = enc(feat, T(g["data/dp_edge_index"], d), None, T(g["hier_enc/x_norm"], d))
+    close(out, g["hier_enc/out"], what="hier_enc out")
+    out.backward(T(g["hier_enc/gout"], d))
+    close(enc.embed.grad, g["hier_enc/d_embed"], what="hier_enc d_embed")
+    close(enc.hgcn.weight.grad, g["hier_enc/d_hgcn.weight"], what="hier_enc d_weight")
+    # the same features as a sparse COO matrix take the valued-SpMM path
+    enc.zero_grad()
+    out2 = enc(feat.to_sparse(), T(g["data/dp_edge_index"], d), None, T(g["hier_enc/x_norm"], d))
+    close(out2, g["hier_enc/out"], what="hier_enc out (sparse features)")
+    out2.backward(T(g["hier_enc/gout"], d))
+    close(enc.embed.grad, g["hier_enc/d_embed"], what="hier_enc d_embed (sparse features)")
+
+
+def test_fm_encoder_with_sparse_drug_features_matches_reference(golden_ablation):
+    """general sparse d_feat (identity + mono side-effect columns, data/utils.py:117-132) and d_norm != 1"""
+    from tip_b200 import layers
+    d, g = dev(), golden_ablation
+    n_prot, n_drug, n_rel, n_mono = int(g["data/n_prot"]), int(g["data/n_drug"]), int(g["data/n_dd_et"]), int(g["fm_mono/n_mono"])
+    fm = layers.FMEncoder(d, n_drug + n_mono, n_rel, n_prot, n_prot, n_drug, prot_drug_dim=16, num_base=8, n_embed=48,
+                          n_hid1=32, n_hid2=16, mod="cat").to(d)
+    with torch.no_grad():
+        for n, p in fm.named_parameters():
+            p.copy_(T(g["fm_mono/param/" + n], d))
+    idx = T(g["fm_mono/feat_index"], d)
+    d_feat = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1], device=d), (n_drug, n_drug + n_mono))
+    z = fm(d_feat, T(g["data/dd_train_idx"], d), T(g["data/dd_train_et"], d), T(g["data/dd_train_range"], d),
+           T(g["fm_mono/d_norm"], d), layers.sparse_id(n_prot).to(d), T(g["data/pp_train_indices"], d),
+           T(g["data/dp_edge_index"], d), None)
+    close(z, g["fm_mono/z"], what="fm_mono z")
+    z.backward(T(g["fm_mono/gz"], d))
+    for n, p in fm.named_parameters():
+        close(p.grad, g["fm_mono/grad/" + n], what="fm_mono grad " + n)
+
+
+def test_gae_default_decoder_is_the_inner_product():
+    from tip_b200 import layers
+    d = dev()
+    gae = layers.MyGAE(torch.nn.Identity())
+    z = torch.randn(50, 16, device=d)
+    ei = torch.randint(0, 50, (2, 300), device=d)
+    close(gae.decoder(z, ei), torch.sigmoid((z[ei[0]] * z[ei[1]]).sum(1)), what="inner product")
+    close(gae.decoder.forward_all(z), torch.sigmoid(z @ z.t()), what="inner product, all pairs")
+
+
+# =============================================================================== edge split (SURVEY 8f rank 2)
+def test_process_edges_on_the_device_matches_reference(golden_layout):
+    """src/utils.py:35-65 on the GPU: the fixture holds what the reference's own process_edges returned under
+    np.random.seed(1111) and the next 64 binomial draws of the stream (position check)"""
+    from tip_b200 import neg_sampling as ns, utils
+    d, g = dev(), golden_layout
+    raw = [T(g[f"raw{i}"], d) for i in range(int(g["n_raw"]))]
+    ns.seed(1111, d)
+    res = utils.process_edges(raw, p=0.9)
+    for name, got in zip(["train_idx", "train_et", "train_range", "test_idx", "test_et", "test_range"], res):
+        assert got.dtype == torch.long and got.is_cuda
+        assert np.array_equal(got.cpu().numpy(), g[name]), name
+    # the stream moved on by exactly two words per raw pair: numpy continues from the device state
+    np.random.set_state(ns.get_state(d))
+    assert np.array_equal(np.random.binomial(1, 0.9, 64), g["binomial_head"])
+
+
+@pytest.mark.parametrize("p", [0.9, 0.5, 0.25, 0.999])
+def test_process_edges_on_the_device_against_the_oracle(p):
+    """ragged relations (empty ones, one pair, 300 k pairs crossing many MT19937 blocks), any split rate, from a
+    mid-block stream position; P-P split of data/utils.py:212-229; everything bit-exact vs oracle.layout_oracle"""
+    from oracle import layout_oracle as lo
+    from tip_b200 import neg_sampling as ns, utils
+    d = dev()
+    gen = np.random.default_rng(17)
+    n = 700
+    sizes = [0, 1, 300_000 if p == 0.9 else 20_000, 0, 0, 977, 5, 0]
+    iu = np.stack(np.triu_indices(n, 1))
+    raw = [iu[:, np.sort(gen.choice(iu.shape[1], size=k, replace=False))].astype(np.int64) for k in sizes]
+    mt = lo.MT19937(4242)
+    mt.words(1000)                                  # mid-block start
+    ns.set_state(mt.get_state(), d)
+    ref = lo.process_edges(mt, raw, p=p) if p > 0.5 else None
+    if ref is None:                                  # the oracle restates the p > 0.5 branch; witness: numpy itself
+        np.random.set_state(ns.get_state(d))
+        res_np = utils.process_edges([torch.from_numpy(r) for r in raw], p=p)
+        ref = tuple(t.numpy() for t in res_np)
+        end_state = np.random.get_state()
+    else:
+        end_state = mt.get_state()
+    got = utils.process_edges([T(r, d) for r in raw], p=p)
+    for name, a, b in zip(["train_idx", "train_et", "train_range", "test_idx", "test_et", "test_range"], got, ref):
+        assert np.array_equal(a.cpu().numpy(), np.asarray(b)), (name, p)
+    st = ns.get_state(d)
+    assert np.array_equal(st[1], end_state[1]) and st[2] == end_state[2]
+    # negatives drawn right after the split continue the same stream (the reference's order: split, then sample)
+    if p == 0.9:
+        from oracle import neg_sampling_oracle as nso
+        neg = ns.typed_negative_sampling(got[3], n, got[5])
+        assert np.array_equal(neg.cpu().numpy(), nso.typed_negative_sampling(mt, np.asarray(ref[3]), n, np.asarray(ref[5])))
+    # P-P split: both directions in, one kept, split, mirrored
+    pp = raw[5]
+    both = np.concatenate([pp, pp[::-1]], axis=1)
+    np.random.set_state(ns.get_state(d))
+    tr_ref, te_ref = utils.process_prot_edge(torch.from_numpy(both), p=0.9)
+    tr, te = utils.process_prot_edge(T(both, d), p=0.9)
+    assert np.array_equal(tr.cpu().numpy(), tr_ref.numpy()) and np.array_equal(te.cpu().numpy(), te_ref.numpy())
+    st, st_np = ns.get_state(d), np.random.get_state()
+    assert np.array_equal(st[1], st_np[1]) and st[2] == st_np[2]
+
+
 # =============================================================================== negative sampler (bit exact)
 def test_negative_sampling_bit_exact(golden_neg):
     from tip_b200 import neg_sampling as ns

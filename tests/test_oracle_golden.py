@@ -164,6 +164,45 @@ def test_full_model_matches_reference(golden_layers):
         assert np.array_equal(neg, g[pre + "neg"])
 
 
+def test_ablation_operators_match_reference(golden_ablation):
+    """the oracle's NNDecoder / HierEncoder / sparse-feature FMEncoder against the reference's own
+    classes (tests/golden/ablation.npz, oracle/make_golden.py:golden_ablation)"""
+    g = golden_ablation
+    n_prot, n_drug = int(g["data/n_prot"]), int(g["data/n_drug"])
+    ei, et = _t(g["data/dd_train_idx"]), _t(g["data/dd_train_et"])
+    perm = _t(g["nn/perm"])
+    w = {k: _t(g["nn/" + k]).requires_grad_(True) for k in ("w1_l1", "w1_l2", "w2_l1", "w2_l2")}
+    z = _t(g["nn/z"]).requires_grad_(True)
+    sc = to.nn_decoder(z, ei[:, perm], et[perm], w["w1_l1"], w["w1_l2"], w["w2_l1"], w["w2_l2"])
+    close(sc.detach(), g["nn/score"])
+    sc.backward(_t(g["nn/gscore"]))
+    close(z.grad, g["nn/dz"])
+    for k, v in w.items():
+        close(v.grad, g["nn/d_" + k])
+    # HierEncoder fed as test/pd_net.py:26 does
+    feat = torch.cat([torch.eye(n_prot), torch.zeros(n_drug, n_prot)])
+    embed, weight = _t(g["hier_enc/embed"]).requires_grad_(True), _t(g["hier_enc/hgcn.weight"]).requires_grad_(True)
+    out = to.hier_encoder(feat, _t(g["data/dp_edge_index"]), _t(g["hier_enc/x_norm"]), embed, weight, n_prot, n_drug)
+    close(out.detach(), g["hier_enc/out"])
+    out.backward(_t(g["hier_enc/gout"]))
+    close(embed.grad, g["hier_enc/d_embed"])
+    close(weight.grad, g["hier_enc/d_hgcn.weight"])
+    # FMEncoder with identity + mono side-effect drug features
+    n_mono = int(g["fm_mono/n_mono"])
+    idx = _t(g["fm_mono/feat_index"])
+    d = {k: _t(g[f"data/{k}"]) for k in ("dd_train_idx", "dd_train_et", "dd_train_range", "pp_train_indices", "dp_edge_index")}
+    d["d_norm"] = _t(g["fm_mono/d_norm"])
+    d["d_feat"] = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n_drug, n_drug + n_mono))
+    names = [n for n in to.TipOracle.param_names if n != "decoder.weight"]
+    params = {n: _t(g["fm_mono/param/" + n[len("encoder."):]]).requires_grad_(True) for n in names}
+    orc = to.TipOracle(params, n_drug, n_prot, mod="cat", structural=True)
+    zz = orc.encode(d)
+    close(zz.detach(), g["fm_mono/z"])
+    zz.backward(_t(g["fm_mono/gz"]))
+    for n in names:
+        close(params[n].grad, g["fm_mono/grad/" + n[len("encoder."):]])
+
+
 def test_eval_oracle_matches_reference_auprc_auroc_ap():
     """oracle/eval_oracle.py against tests/golden/eval.npz = outputs of the reference's own src/utils.py:86-93
     (scikit-learn) on seeded scores with heavy ties, saturated scores and a one-pair relation"""

@@ -65,6 +65,22 @@ SIGNATURES = {
     "tipb_eval_auprc_auroc_ap": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "tipb_adam_max_tensors": (C.c_int, []),
     "tipb_adam_step": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, _p, _p]),
+    "tipb_gemm": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _p]),
+    "tipb_gemm_tn_workspace_bytes": (_sz, [_i64, _i64]),
+    "tipb_gemm_tn": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "tipb_relu_grad_colsum_workspace_bytes": (_sz, [_i64]),
+    "tipb_relu_grad_colsum": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "tipb_transpose": (C.c_int, [_p, _i64, _i64, _p, _p]),
+    "tipb_drug_input_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
+    "tipb_drug_input_bwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "tipb_scale2": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _p]),
+    "tipb_fill_zero": (C.c_int, [_p, _sz, _p]),
+    "tipb_nn_decoder_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p]),
+    "tipb_nn_decoder_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p]),
+    "tipb_spmm_values": (C.c_int, [_p, _i64, _i64, _p, _p, _i32, _p, _p]),
+    "tipb_edge_split_workspace_bytes": (_sz, [_i64]),
+    "tipb_edge_split_mask": (C.c_int, [_p, _p, _i64, _i64, C.c_double, C.c_double, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_edge_split_emit": (C.c_int, [_p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "tipb_mt19937_seed": (C.c_int, [_p, _u32, _p]),
     "tipb_mt19937_stream_words": (_i64, [_i64]),
     "tipb_mt19937_generate": (C.c_int, [_p, _p, _i64, _p]),

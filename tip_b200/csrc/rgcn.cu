@@ -328,11 +328,12 @@ k_atb_tiled(const float* __restrict__ A, const float* __restrict__ Bm, int K, in
     }
 }
 
-int atb_launch(const float* A, const float* Bm, int K, int M, int N, float* out, float* partial_ws, cudaStream_t s) {
+int atb_launch(const float* A, const float* Bm, int K, int M, int N, float* out, float* partial_ws, cudaStream_t s,
+               int slice_cap) {
     if (N == 16 || N == 32 || N == 64 || N == 128) {
         const int tiles = (int)ceil_div(M, ATBT_ROWS);
         int k_slices = (int)ceil_div(2 * sm_count(), tiles);
-        if (k_slices > 32) k_slices = 32;
+        if (k_slices > slice_cap) k_slices = slice_cap;
         const int max_slices = (int)ceil_div(K > 0 ? K : 1, ATBT_KC);
         if (k_slices > max_slices) k_slices = max_slices;
         const dim3 grid(tiles, k_slices);
@@ -347,12 +348,15 @@ int atb_launch(const float* A, const float* Bm, int K, int M, int N, float* out,
     // enough CTAs to cover the machine, but never more slices than rows of K
     int tiles = (int)ceil_div(M, ATB_ROWS);
     int k_slices = (int)ceil_div(2 * sm_count(), tiles);
-    if (k_slices > 32) k_slices = 32;
+    if (k_slices > slice_cap) k_slices = slice_cap;
     if (k_slices > K) k_slices = K > 0 ? K : 1;
     k_atb<<<dim3(tiles, k_slices), 256, 0, s>>>(A, Bm, K, M, N, k_slices, partial_ws);
     k_sum_slices<<<(unsigned)ceil_div(int64_t(M) * N, 256), 256, 0, s>>>(partial_ws, int64_t(M) * N, k_slices, out);
     TIPB_CHECK_LAUNCH("atb");
     return TIPB_OK;
+}
+int atb_launch(const float* A, const float* Bm, int K, int M, int N, float* out, float* partial_ws, cudaStream_t s) {
+    return atb_launch(A, Bm, K, M, N, out, partial_ws, s, 32);
 }
 size_t atb_ws_floats(int M, int N) { return size_t(32) * M * N; }
 

@@ -187,16 +187,16 @@ class GCNConv(nn.Module):
             if key not in self._identity_ok:
                 self._identity_ok[key] = is_sparse_identity(x)     # one-time check (host sync at setup)
             if self._identity_ok[key]:
-                return self.lin.weight.t().contiguous()            # I @ W^T
-            return torch.sparse.mm(x, self.lin.weight.t())         # general sparse features (not on the TIP path)
-        return x @ self.lin.weight.t()
+                return ops.transpose2d(self.lin.weight)            # I @ W^T
+            return ops.sparse_matmul(x, ops.transpose2d(self.lin.weight))   # general sparse features
+        return ops.matmul(x, self.lin.weight, trans_b=True)
 
-    def forward(self, x, edge_index, _fused_relu=False):
+    def forward(self, x, edge_index, _fused_relu=False, _pad_rows=0):
         assert edge_index.dtype == torch.long and edge_index.dim() == 2 and edge_index.size(0) == 2
         if not edge_index.is_cuda:
             raise TipbError("GCNConv: CUDA tensors only -- tip_b200 has no CPU fallback")
         plan_dst, plan_src, dis = self._graph(edge_index, x.size(0))
-        return ops.gcn_spmm(self._linear(x), self.bias, plan_dst, plan_src, dis, relu=_fused_relu)
+        return ops.gcn_spmm(self._linear(x), self.bias, plan_dst, plan_src, dis, relu=_fused_relu, pad_rows=_pad_rows)
 
 
 # =============================================================================== encoders
@@ -209,9 +209,9 @@ class PPEncoder(nn.Module):
         self.conv1 = GCNConv(in_dim, hid1, cached=True)
         self.conv2 = GCNConv(hid1, hid2, cached=True)
 
-    def forward(self, x, edge_index):
+    def forward(self, x, edge_index, _pad_rows=0):
         x = self.conv1(x, edge_index, _fused_relu=True)      # bias + ReLU fused into the SpMM epilogue
-        return self.conv2(x, edge_index)
+        return self.conv2(x, edge_index, _pad_rows=_pad_rows)   # (+ zero rows below: the caller's cat with `hdrug`)
 
 
 class FMEncoder(nn.Module):
@@ -230,6 +230,7 @@ class FMEncoder(nn.Module):
         self.embed = Param(torch.Tensor(in_dim_drug, n_embed))
         self.hgcn = MyHierarchyConv(self.pp_encoder.out_dim, prot_drug_dim, uni_num_prot, uni_num_drug)
         self.hdrug = torch.zeros((self.uni_num_drug, self.pp_encoder.out_dim)).to(device)
+        self._hdrug_version = self.hdrug._version     # still all zeros while untouched: the cat below is then fused
         rgcn_in_dim = n_embed + self.hgcn.out_dim if mod == "cat" else n_embed
         self.rgcn1 = MyRGCNConv2(rgcn_in_dim, n_hid1, num_dd_et, num_base, after_relu=False)
         self.rgcn2 = MyRGCNConv2(n_hid1, n_hid2, num_dd_et, num_base, after_relu=True)
@@ -246,16 +247,23 @@ class FMEncoder(nn.Module):
                 self._identity_ok[key] = is_sparse_identity(x_drug)
             if self._identity_ok[key]:
                 return self.embed                                   # I @ embed
-            return torch.sparse.mm(x_drug, self.embed)
-        return torch.matmul(x_drug, self.embed)
+            return ops.sparse_matmul(x_drug, self.embed)            # general sparse drug features (data/utils.py:117-132)
+        return ops.matmul(x_drug, self.embed)
+
+    def drug_input(self, x_drug, d_norm, x_prot, pp_edge_index, dp_edge_index, dp_range_list):
+        """src/layers.py:529-547: everything in front of the two R-GCN layers"""
+        if self.hdrug._version == self._hdrug_version and self.hdrug.device == pp_edge_index.device:
+            # torch.cat((x_prot, hdrug)) with hdrug == 0: the second GCN layer writes into a buffer with zero rows below
+            x_prot = self.pp_encoder(x_prot, pp_edge_index, _pad_rows=self.uni_num_drug)
+        else:
+            x_prot = self.pp_encoder(x_prot, pp_edge_index)
+            x_prot = torch.cat((x_prot, self.hdrug.to(x_prot.device)))
+        x_prot = self.hgcn(x_prot, dp_edge_index, dp_range_list)
+        return ops.drug_input(self._embed(x_drug), d_norm, x_prot, self.mod)   # / d_norm, then cat | add
 
     def forward(self, x_drug, dd_edge_index, dd_edge_type, dd_range_list, d_norm, x_prot, pp_edge_index,
                 dp_edge_index, dp_range_list):
-        x_prot = self.pp_encoder(x_prot, pp_edge_index)
-        x_prot = torch.cat((x_prot, self.hdrug.to(x_prot.device)))
-        x_prot = self.hgcn(x_prot, dp_edge_index, dp_range_list)
-        x_drug = self._embed(x_drug) / d_norm.view(-1, 1)
-        x_drug = torch.cat((x_drug, x_prot), dim=1) if self.mod == "cat" else x_drug + x_prot
+        x_drug = self.drug_input(x_drug, d_norm, x_prot, pp_edge_index, dp_edge_index, dp_range_list)
         x_drug = self.rgcn1(x_drug, dd_edge_index, dd_edge_type, dd_range_list, _fused_relu=True)
         return self.rgcn2(x_drug, dd_edge_index, dd_edge_type, dd_range_list)
 
@@ -269,7 +277,49 @@ class FMEncoderCat(FMEncoder):
                          num_base, n_embed, n_hid1, n_hid2, mod="cat")
 
 
+class HierEncoder(nn.Module):
+    """source embedding -> hierarchy conv onto the targets (src/layers.py:556-575; the PR-HMP-NN ablation)"""
+
+    def __init__(self, source_dim, embed_dim, target_dim, uni_num_source, uni_num_target):
+        super().__init__()
+        self.embed = Param(torch.Tensor(source_dim, embed_dim))
+        self.hgcn = MyHierarchyConv(embed_dim, target_dim, uni_num_source, uni_num_target)
+        self._identity_ok = {}
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embed.data.normal_()
+
+    def forward(self, source_feat, edge_index, range_list, x_norm):
+        if source_feat.is_sparse:
+            key = (source_feat._indices().data_ptr(), tuple(source_feat.shape))
+            if key not in self._identity_ok:
+                self._identity_ok[key] = is_sparse_identity(source_feat)
+            x = self.embed if self._identity_ok[key] else ops.sparse_matmul(source_feat, self.embed)
+        else:
+            x = ops.matmul(source_feat, self.embed)
+        x = ops.row_scale(x, x_norm)                      # x / x_norm.view(-1, 1)
+        return self.hgcn(x, edge_index, range_list)
+
+
 # =============================================================================== decoder
+class InnerProductDecoder(nn.Module):
+    """torch_geometric 2.0.1 InnerProductDecoder (imported at src/layers.py:2, MyGAE's default at :258):
+    sigmoid(z_i . z_j) -- the DistMult scorer with a single all-ones relation"""
+
+    def _ones(self, z):
+        return torch.ones((1, z.shape[1]), dtype=torch.float32, device=z.device)
+
+    def forward(self, z, edge_index, sigmoid=True):
+        _require_cuda(z, "InnerProductDecoder")
+        et = torch.zeros(edge_index.shape[1], dtype=torch.long, device=z.device)
+        return ops.decoder_score(z, self._ones(z), edge_index, et, sigmoid)
+
+    def forward_all(self, z, sigmoid=True):
+        _require_cuda(z, "InnerProductDecoder")
+        return ops.decoder_sweep(z, self._ones(z), sigmoid)[0]
+
+
 class MultiInnerProductDecoder(nn.Module):
     """DistMult scorer z_i^T diag(w_r) z_j (src/layers.py:581-595)"""
 
@@ -291,16 +341,38 @@ class MultiInnerProductDecoder(nn.Module):
         self.weight.data.normal_(std=1 / np.sqrt(self.in_dim))
 
 
+class NNDecoder(nn.Module):
+    """two-layer per-endpoint scorer (src/layers.py:598-637; the DR-NN / PR-HMP-NN ablations):
+    sigmoid( relu(z_i w1_l1) . w1_l2[r] + relu(z_j w2_l1) . w2_l2[r] )"""
+
+    def __init__(self, in_dim, num_uni_edge_type, l1_dim=16):
+        super().__init__()
+        self.l1_dim = l1_dim
+        self.w1_l1 = Param(torch.Tensor(in_dim, l1_dim))
+        self.w1_l2 = Param(torch.Tensor(num_uni_edge_type, l1_dim))
+        self.w2_l1 = Param(torch.Tensor(in_dim, l1_dim))
+        self.w2_l2 = Param(torch.Tensor(num_uni_edge_type, l1_dim))
+        self.reset_parameters()
+
+    def forward(self, z, edge_index, edge_type):
+        _require_cuda(z, "NNDecoder")
+        return ops.nn_decoder_score(z, self.w1_l1, self.w1_l2, self.w2_l1, self.w2_l2, edge_index, edge_type)
+
+    def reset_parameters(self):     # draw order w1_l1, w2_l1, w1_l2, w2_l2 (src/layers.py:633-637)
+        self.w1_l1.data.normal_()
+        self.w2_l1.data.normal_()
+        self.w1_l2.data.normal_(std=1 / np.sqrt(self.l1_dim))
+        self.w2_l2.data.normal_(std=1 / np.sqrt(self.l1_dim))
+
+
 # =============================================================================== training wrapper
 class MyGAE(nn.Module):
-    """src/layers.py:253-258 (the TIP path always passes a decoder)"""
+    """src/layers.py:253-258"""
 
     def __init__(self, encoder, decoder=None):
         super().__init__()
         self.encoder = encoder
-        if decoder is None:
-            raise TipbError("MyGAE without a decoder needs torch_geometric's InnerProductDecoder (not on the TIP path)")
-        self.decoder = decoder
+        self.decoder = InnerProductDecoder() if decoder is None else decoder
 
 
 class Setting(object):
@@ -345,12 +417,12 @@ class TIP(nn.Module):
                 data_dict = pickle.load(f)
         data_dict = dict(data_dict)
         if sp_rate != 0.9:
-            # same single numpy-compatible stream as the reference: hand it to numpy for the split, take it back
-            np.random.set_state(_ns.get_state(self.device))
-            (data_dict["dd_train_idx"], data_dict["dd_train_et"], data_dict["dd_train_range"],
-             data_dict["dd_test_idx"], data_dict["dd_test_et"], data_dict["dd_test_range"]) = \
-                process_edges(data_dict["dd_edge_index"], p=sp_rate)
-            _ns.set_state(np.random.get_state(), self.device)
+            # src/layers.py:282-286: re-split with the requested rate.  The split runs on the device and draws from the
+            # device-side numpy-compatible stream (the reference draws from np.random at this point)
+            with torch.cuda.device(self.device):
+                raw = [torch.as_tensor(e).to(self.device) for e in data_dict["dd_edge_index"]]
+                (data_dict["dd_train_idx"], data_dict["dd_train_et"], data_dict["dd_train_range"],
+                 data_dict["dd_test_idx"], data_dict["dd_test_et"], data_dict["dd_test_range"]) = process_edges(raw, p=sp_rate)
         data = _Data(data_dict, self.device)
         data.dd_train_range = data.dd_train_range.to(torch.long)
         data.dd_test_range = data.dd_test_range.to(torch.long)

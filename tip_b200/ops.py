@@ -122,6 +122,8 @@ def clear_plan_cache():
     _pair_plans.clear()
     _item_tables.clear()
     _mirror_cache.clear()
+    _edge_plans.clear()
+    _sparse_feats.clear()
 
 
 def _tensor_key(t):
@@ -222,31 +224,39 @@ def rgcn_conv(x, basis, att, root, plan_dst, plan_src, bias=None, relu=False):
 # ----------------------------------------------------------------------------- GCN SpMM
 class _GCNSpmmFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bias, plan_dst, plan_src, dis, relu):
+    def forward(ctx, x, bias, plan_dst, plan_src, dis, relu, pad_rows):
         x = _f32c(x)
         n, f = x.shape
-        out = torch.empty_like(x)
-        check(lib().tipb_gcn_spmm(ptr(plan_dst.buf), plan_dst.n_entries, n, ptr(dis), ptr(dis), ptr(x),
-                                  None if bias is None else ptr(_f32c(bias)), f, int(relu), ptr(out), stream()),
-              "gcn_spmm")
-        ctx.plan_src, ctx.dis, ctx.relu, ctx.has_bias = plan_src, dis, relu, bias is not None
+        L = lib()
+        # `pad_rows` zero rows under the result: torch.cat((x_prot, hdrug)) of src/layers.py:533 without the copy
+        out = torch.empty((n + pad_rows, f), dtype=torch.float32, device=x.device)
+        check(L.tipb_gcn_spmm(ptr(plan_dst.buf), plan_dst.n_entries, n, ptr(dis), ptr(dis), ptr(x),
+                              None if bias is None else ptr(_f32c(bias)), f, int(relu), ptr(out), stream()), "gcn_spmm")
+        if pad_rows:
+            check(L.tipb_fill_zero(out.data_ptr() + n * f * 4, pad_rows * f * 4, stream()), "fill_zero")
+        ctx.plan_src, ctx.dis, ctx.relu, ctx.has_bias, ctx.n = plan_src, dis, relu, bias is not None, n
         if relu:
             ctx.save_for_backward(out)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        grad_out = _f32c(grad_out)
-        if ctx.relu:
-            (out,) = ctx.saved_tensors
-            grad_out = grad_out * (out > 0)
-        n, f = grad_out.shape
-        d_x = torch.empty_like(grad_out)
+        grad_out = _f32c(grad_out)          # rows beyond n (the zero rows) take no gradient
+        n, f = ctx.n, grad_out.shape[1]
+        L = lib()
+        d_bias = torch.empty(f, dtype=torch.float32, device=grad_out.device) if ctx.has_bias else None
+        g = grad_out
+        if ctx.relu or ctx.has_bias:        # ReLU mask and bias gradient in one library call
+            (out,) = ctx.saved_tensors if ctx.relu else (None,)
+            g = torch.empty((n, f), dtype=torch.float32, device=grad_out.device) if ctx.relu else grad_out
+            ws = workspace(L.tipb_relu_grad_colsum_workspace_bytes(f), grad_out.device, "colsum")
+            check(L.tipb_relu_grad_colsum(ptr(grad_out), ptr(out), n, f, ptr(g) if ctx.relu else None, ptr(d_bias),
+                                          ptr(ws), ws.numel(), stream()), "relu_grad_colsum")
+        d_x = torch.empty((n, f), dtype=torch.float32, device=grad_out.device)
         plan = ctx.plan_src
-        check(lib().tipb_gcn_spmm(ptr(plan.buf), plan.n_entries, n, ptr(ctx.dis), ptr(ctx.dis), ptr(grad_out), None, f, 0,
-                                  ptr(d_x), stream()), "gcn_spmm(bwd)")
-        d_bias = grad_out.sum(dim=0) if ctx.has_bias else None
-        return d_x, d_bias, None, None, None, None
+        check(L.tipb_gcn_spmm(ptr(plan.buf), plan.n_entries, n, ptr(ctx.dis), ptr(ctx.dis), ptr(g), None, f, 0,
+                              ptr(d_x), stream()), "gcn_spmm(bwd)")
+        return d_x, d_bias, None, None, None, None, None
 
 
 def gcn_norm(plan_dst):
@@ -257,7 +267,7 @@ def gcn_norm(plan_dst):
 
 
 @_guarded
-def gcn_spmm(x, bias, plan_dst, plan_src, dis, relu=False):
+def gcn_spmm(x, bias, plan_dst, plan_src, dis, relu=False, pad_rows=0):
     f = x.shape[1]
     fp = _next_pow2(f)
     if fp > 128:
@@ -265,8 +275,126 @@ def gcn_spmm(x, bias, plan_dst, plan_src, dis, relu=False):
     if fp != f:
         x = F.pad(x, (0, fp - f))
         bias = None if bias is None else F.pad(bias, (0, fp - f))
-    out = _GCNSpmmFunction.apply(x, bias, plan_dst, plan_src, dis, relu)
+    out = _GCNSpmmFunction.apply(x, bias, plan_dst, plan_src, dis, relu, int(pad_rows))
     return out if fp == f else out[:, :f]
+
+
+# ----------------------------------------------------------------------------- small dense products
+class _MatmulFunction(torch.autograd.Function):
+    """y = x @ w (w [k, n]) or x @ w^T (w [n, k], torch.nn.Linear layout) (+ bias) (+ ReLU) through tipb_gemm"""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, trans_b, relu):
+        x, w = _f32c(x), _f32c(w)
+        m, k = x.shape
+        n = w.shape[0] if trans_b else w.shape[1]
+        assert (w.shape[1] if trans_b else w.shape[0]) == k, "matmul: inner dimensions differ"
+        y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+        check(lib().tipb_gemm(ptr(x), ptr(w), None if bias is None else ptr(_f32c(bias)), m, n, k, int(trans_b), int(relu),
+                              ptr(y), stream()), "gemm")
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.trans_b, ctx.relu, ctx.has_bias = trans_b, relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        gy = _f32c(gy)
+        m, k = x.shape
+        n = gy.shape[1]
+        L = lib()
+        g, d_bias = gy, None
+        if ctx.relu or ctx.has_bias:
+            d_bias = torch.empty(n, dtype=torch.float32, device=gy.device) if ctx.has_bias else None
+            g = torch.empty_like(gy) if ctx.relu else gy
+            ws = workspace(L.tipb_relu_grad_colsum_workspace_bytes(n), gy.device, "colsum")
+            check(L.tipb_relu_grad_colsum(ptr(gy), ptr(y) if ctx.relu else None, m, n, ptr(g) if ctx.relu else None,
+                                          ptr(d_bias), ptr(ws), ws.numel(), stream()), "relu_grad_colsum")
+        d_x = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_x = torch.empty_like(x)       # g w^T (w [k,n]) or g w (w [n,k])
+            check(L.tipb_gemm(ptr(g), ptr(w), None, m, k, n, int(not ctx.trans_b), 0, ptr(d_x), stream()), "gemm(d_x)")
+        if ctx.needs_input_grad[1]:
+            d_w = torch.empty_like(w)
+            a, b, mm, nn = (g, x, n, k) if ctx.trans_b else (x, g, k, n)     # g^T x [n,k]  |  x^T g [k,n]
+            ws = workspace(L.tipb_gemm_tn_workspace_bytes(mm, nn), gy.device, "gemm_tn")
+            check(L.tipb_gemm_tn(ptr(a), ptr(b), m, mm, nn, ptr(d_w), ptr(ws), ws.numel(), stream()), "gemm_tn")
+        return d_x, d_w, d_bias, None, None
+
+
+@_guarded
+def matmul(x, w, trans_b=False, bias=None, relu=False):
+    """x [m,k] times w [k,n] (or w^T with w [n,k] when trans_b), optional bias and ReLU, with gradients -- library kernels"""
+    if not x.is_cuda:
+        raise _lib.TipbError("matmul: CUDA tensors only -- tip_b200 has no CPU fallback")
+    return _MatmulFunction.apply(x, w, bias, bool(trans_b), bool(relu))
+
+
+class _TransposeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        out = torch.empty((x.shape[1], x.shape[0]), dtype=torch.float32, device=x.device)
+        check(lib().tipb_transpose(ptr(x), x.shape[0], x.shape[1], ptr(out), stream()), "transpose")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        out = torch.empty((g.shape[1], g.shape[0]), dtype=torch.float32, device=g.device)
+        check(lib().tipb_transpose(ptr(g), g.shape[0], g.shape[1], ptr(out), stream()), "transpose")
+        return out
+
+
+@_guarded
+def transpose2d(x):
+    """contiguous x^T (and a contiguous gradient in the parameter's own layout)"""
+    return _TransposeFunction.apply(x)
+
+
+class _DrugInputFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e, d_norm, h, mode):
+        e, h, d_norm = _f32c(e), _f32c(h), _f32c(d_norm.reshape(-1))
+        n, fe = e.shape
+        fh = h.shape[1]
+        assert h.shape[0] == n and d_norm.numel() == n
+        out = torch.empty((n, fe + fh if mode == 0 else fe), dtype=torch.float32, device=e.device)
+        check(lib().tipb_drug_input_fwd(ptr(e), ptr(d_norm), ptr(h), n, fe, fh, mode, ptr(out), stream()), "drug_input_fwd")
+        ctx.save_for_backward(d_norm)
+        ctx.dims = (n, fe, fh, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_norm,) = ctx.saved_tensors
+        n, fe, fh, mode = ctx.dims
+        g = _f32c(g)
+        d_e = torch.empty((n, fe), dtype=torch.float32, device=g.device)
+        d_h = torch.empty((n, fh), dtype=torch.float32, device=g.device)
+        check(lib().tipb_drug_input_bwd(ptr(g), ptr(d_norm), n, fe, fh, mode, ptr(d_e), ptr(d_h), stream()), "drug_input_bwd")
+        return d_e, None, d_h, None
+
+
+@_guarded
+def drug_input(embed_out, d_norm, hier_out, mod):
+    """FMEncoder's glue (src/layers.py:541-547): embed_out / d_norm.view(-1, 1), then cat(dim=1) | + with hier_out"""
+    return _DrugInputFunction.apply(embed_out, d_norm, hier_out, 0 if mod == "cat" else 1)
+
+
+def row_scale(x, norm):
+    """x / norm.view(-1, 1) (HierEncoder, src/layers.py:572): the drug-input kernel with an empty second block"""
+    empty = torch.empty((x.shape[0], 0), dtype=torch.float32, device=x.device)
+    return _DrugInputFunction.apply(x, norm, empty, 0)
+
+
+def _scale_pair(d_z, d_w, grad_loss):
+    """(d_z, d_w) * grad_loss (a device scalar) in one library launch"""
+    o_z, o_w = torch.empty_like(d_z), torch.empty_like(d_w)
+    with torch.cuda.device(d_z.device):
+        check(lib().tipb_scale2(ptr(d_z), d_z.numel(), ptr(d_w), d_w.numel(), ptr(_f32c(grad_loss.reshape(1))), ptr(o_z),
+                                ptr(o_w), stream()), "scale2")
+    return o_z, o_w
 
 
 # ----------------------------------------------------------------------------- hierarchy conv
@@ -402,7 +530,7 @@ class _BCELossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         d_z, d_w = ctx.saved_tensors
-        return d_z * grad_loss, d_w * grad_loss, None, None, None
+        return _scale_pair(d_z, d_w, grad_loss) + (None, None, None)
 
 
 _mirror_cache = {}
@@ -571,7 +699,7 @@ class _PairBCEFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         d_z, d_w = ctx.saved_tensors
-        return d_z * grad_loss, d_w * grad_loss, None, None, None
+        return _scale_pair(d_z, d_w, grad_loss) + (None, None, None)
 
 
 @_guarded
@@ -602,6 +730,124 @@ def decoder_sweep(z, weight, sigmoid=True):
     return out
 
 
+# ----------------------------------------------------------------------------- ablation operators
+_edge_plans = {}     # (n_edges, n_nodes, n_rel, device) -> [plan_by_src, plan_by_dst]: one pair of buffers per shape
+
+
+def _edge_plan_pair(edge_index, edge_type, n_nodes, n_rel):
+    key = (int(edge_index.shape[1]), int(n_nodes), int(n_rel), str(edge_index.device))
+    pair = _edge_plans.get(key)
+    if pair is None:
+        while len(_edge_plans) >= 4:
+            _edge_plans.pop(next(iter(_edge_plans)))
+        pair = _edge_plans[key] = [TypedCSR(edge_index.shape[1], n_nodes, n_rel, edge_index.device, by_src=b) for b in (True, False)]
+    for plan in pair:
+        plan.build(edge_index, edge_type)
+    return pair
+
+
+class _NNDecoderGather(torch.autograd.Function):
+    """score[e] = act(table_a[i_e, r_e] + table_b[j_e, r_e]); the table gradients are segment sums (no atomics)"""
+
+    @staticmethod
+    def forward(ctx, table_a, table_b, edge_index, edge_type, sigmoid):
+        table_a, table_b = _f32c(table_a), _f32c(table_b)
+        edge_index, edge_type = _i64c(edge_index), _i64c(edge_type)
+        n_nodes, n_rel = table_a.shape
+        n_edges = edge_index.shape[1]
+        out = torch.empty(n_edges, dtype=torch.float32, device=table_a.device)
+        check(lib().tipb_nn_decoder_fwd(ptr(table_a), ptr(table_b), ptr(edge_index), ptr(edge_type), n_edges, n_nodes, n_rel,
+                                        int(sigmoid), ptr(out), stream()), "nn_decoder_fwd")
+        ctx.save_for_backward(out, edge_index, edge_type)
+        ctx.dims, ctx.sigmoid = (n_nodes, n_rel), sigmoid
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out, edge_index, edge_type = ctx.saved_tensors
+        n_nodes, n_rel = ctx.dims
+        n_edges = edge_index.shape[1]
+        by_src, by_dst = _edge_plan_pair(edge_index, edge_type, n_nodes, n_rel)
+        d_a = torch.empty((n_nodes, n_rel), dtype=torch.float32, device=out.device)
+        d_b = torch.empty_like(d_a)
+        g_ws = torch.empty(max(n_edges, 1), dtype=torch.float32, device=out.device)
+        check(lib().tipb_nn_decoder_bwd(ptr(by_src.buf), ptr(by_dst.buf), n_edges, n_nodes, n_rel, ptr(_f32c(grad_out)),
+                                        ptr(out), int(ctx.sigmoid), ptr(d_a), ptr(d_b), ptr(g_ws), stream()), "nn_decoder_bwd")
+        return d_a, d_b, None, None, None
+
+
+@_guarded
+def nn_decoder_score(z, w1_l1, w1_l2, w2_l1, w2_l2, edge_index, edge_type, sigmoid=True):
+    """NNDecoder.forward (src/layers.py:618-631).  The hidden layers are per NODE (relu(z W) does not depend on the
+    edge), and so are the per-(node, relation) dot products: two [N, l1] and two [N, R] dense products replace the
+    reference's E x l1 gathers; the per-edge work is the gather of two scalars."""
+    if not z.is_cuda:
+        raise _lib.TipbError("NNDecoder: CUDA tensors only -- tip_b200 has no CPU fallback")
+    h1 = matmul(z, w1_l1, relu=True)
+    h2 = matmul(z, w2_l1, relu=True)
+    table_a = matmul(h1, w1_l2, trans_b=True)
+    table_b = matmul(h2, w2_l2, trans_b=True)
+    return _NNDecoderGather.apply(table_a, table_b, edge_index, edge_type, sigmoid)
+
+
+class SparseFeatures(object):
+    """index structures of a sparse COO feature matrix S [n_rows, n_cols] (general drug features, data/utils.py:117-132):
+    typed CSRs (n_rel = 1) of the entries by row (forward, S @ dense) and by column (gradient, S^T @ g)"""
+
+    def __init__(self, x):
+        x = x.coalesce()
+        idx, self.values = x.indices(), _f32c(x.values())
+        self.n_rows, self.n_cols = int(x.shape[0]), int(x.shape[1])
+        n = max(self.n_rows, self.n_cols)
+        # "edge" col -> row: by-target plan groups the entries by output row, by-source plan by column
+        edges = torch.stack([idx[1], idx[0]]).contiguous()
+        self.nnz = int(edges.shape[1])
+        self.by_row = TypedCSR(self.nnz, n, 1, x.device, by_src=False).build(edges).check_status()
+        self.by_col = TypedCSR(self.nnz, n, 1, x.device, by_src=True).build(edges).check_status()
+        self.n = n
+
+
+class _SpmmValuesFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dense, feats):
+        dense = _f32c(dense)
+        assert dense.shape[0] == feats.n_cols
+        f = dense.shape[1]
+        out = torch.empty((feats.n, f), dtype=torch.float32, device=dense.device)
+        check(lib().tipb_spmm_values(ptr(feats.by_row.buf), feats.nnz, feats.n, ptr(feats.values), ptr(dense), f, ptr(out),
+                                     stream()), "spmm_values")
+        ctx.feats = feats
+        return out[:feats.n_rows]
+
+    @staticmethod
+    def backward(ctx, g):
+        feats = ctx.feats
+        f = g.shape[1]
+        gp = g
+        if feats.n != feats.n_rows:       # rows of the square index space beyond n_rows have no entries
+            gp = torch.zeros((feats.n, f), dtype=torch.float32, device=g.device)
+            gp[:feats.n_rows] = g
+        out = torch.empty((feats.n, f), dtype=torch.float32, device=g.device)
+        check(lib().tipb_spmm_values(ptr(feats.by_col.buf), feats.nnz, feats.n, ptr(feats.values), ptr(_f32c(gp)), f, ptr(out),
+                                     stream()), "spmm_values(bwd)")
+        return out[:feats.n_cols], None
+
+
+_sparse_feats = {}
+
+
+@_guarded
+def sparse_matmul(x_sparse, dense):
+    """torch.matmul(x_sparse, dense) for a sparse COO feature matrix, through the library (plans cached per tensor)"""
+    key = (x_sparse._indices().data_ptr(), x_sparse._values().data_ptr(), tuple(x_sparse.shape))
+    hit = _sparse_feats.get(key)
+    if hit is None:
+        if len(_sparse_feats) > 8:
+            _sparse_feats.clear()
+        hit = _sparse_feats[key] = (SparseFeatures(x_sparse), x_sparse)
+    return _SpmmValuesFunction.apply(dense, hit[0])
+
+
 def check_cumulative_ranges(range_list, n_edges):
     """range_list must be the cumulative [start, end) table of src/utils.py:26-32 tiling [0, n_edges)"""
     rl = np.asarray(range_list.detach().cpu() if torch.is_tensor(range_list) else range_list).astype(np.int64)
@@ -630,5 +876,5 @@ def eval_auprc_auroc_ap(pos_score, neg_score, range_list):
     return record
 
 
-__all__ = ["eval_auprc_auroc_ap", "TypedCSR", "cached_plan", "rgcn_conv", "gcn_norm", "gcn_spmm", "hier_conv", "decoder_score", "bce_loss",
+__all__ = ["eval_auprc_auroc_ap", "matmul", "transpose2d", "drug_input", "nn_decoder_score", "sparse_matmul", "TypedCSR", "cached_plan", "rgcn_conv", "gcn_norm", "gcn_spmm", "hier_conv", "decoder_score", "bce_loss",
            "decoder_sweep", "workspace", "math"]

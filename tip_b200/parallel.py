@@ -269,12 +269,8 @@ class ShardedTIP(TIP):
         return torch.relu(out) if relu else out
 
     def _drug_input(self):
-        d, enc = self.data, self.encoder
-        x_prot = enc.pp_encoder(d.p_feat, d.pp_train_indices)
-        x_prot = torch.cat((x_prot, enc.hdrug.to(x_prot.device)))
-        x_prot = enc.hgcn(x_prot, d.dp_edge_index, d.dp_range_list)
-        x_drug = enc._embed(d.d_feat) / d.d_norm.view(-1, 1)
-        return torch.cat((x_drug, x_prot), dim=1) if enc.mod == "cat" else x_drug + x_prot
+        d = self.data
+        return self.encoder.drug_input(d.d_feat, d.d_norm, d.p_feat, d.pp_train_indices, d.dp_edge_index, d.dp_range_list)
 
     def _encode(self):
         enc = self.encoder
@@ -417,7 +413,7 @@ class ShardedDDNet(ShardedTIP):
 
     def _drug_input(self):
         # d_feat is the sparse identity (test/dd_net_scalable.py:43): x @ embed == embed; x_norm = ones
-        return self.encoder.embed / self.data.d_norm.view(-1, 1)
+        return ops.row_scale(self.encoder.embed, self.data.d_norm)
 
     def _encode(self):
         enc = self.encoder
