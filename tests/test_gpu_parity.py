@@ -392,7 +392,7 @@ def test_process_edges_on_the_device_against_the_oracle(p):
     from tip_b200 import neg_sampling as ns, utils
     d = dev()
     gen = np.random.default_rng(17)
-    n = 700
+    n = 1000
     sizes = [0, 1, 300_000 if p == 0.9 else 20_000, 0, 0, 977, 5, 0]
     iu = np.stack(np.triu_indices(n, 1))
     raw = [iu[:, np.sort(gen.choice(iu.shape[1], size=k, replace=False))].astype(np.int64) for k in sizes]

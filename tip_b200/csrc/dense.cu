@@ -121,12 +121,15 @@ k_mask_colsum(const float* __restrict__ gy, const float* __restrict__ mask_ref, 
         partial[size_t(blockIdx.y) * N + col] = t;
     }
 }
-__global__ void k_colsum_finish(const float* __restrict__ partial, int n_slices, int N, float* __restrict__ db) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: lane l adds slices l, l + 32, ... in order, then a fixed shuffle tree
+__global__ void __launch_bounds__(256)
+k_colsum_finish(const float* __restrict__ partial, int n_slices, int N, float* __restrict__ db) {
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (col >= N) return;
     float t = 0.f;
-    for (int k = 0; k < n_slices; ++k) t += partial[size_t(k) * N + col];
-    db[col] = t;
+    for (int k = lane; k < n_slices; k += 32) t += partial[size_t(k) * N + col];
+    t = warp_sum(t);
+    if (lane == 0) db[col] = t;
 }
 
 // ------------------------------------------------------------------------------------------------ NN decoder
@@ -278,7 +281,7 @@ int tipb_relu_grad_colsum(const float* gy, const float* relu_out, int64_t m, int
     const int rows_per_slice = (int)ceil_div(m > 0 ? m : 1, n_slices);
     const dim3 grid((unsigned)ceil_div(n, 32), (unsigned)n_slices);
     k_mask_colsum<<<grid, 256, 0, s>>>(gy, relu_out, m, (int)n, rows_per_slice, g, d_bias ? (float*)ws : nullptr);
-    if (d_bias) k_colsum_finish<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>((const float*)ws, n_slices, (int)n, d_bias);
+    if (d_bias) k_colsum_finish<<<(unsigned)ceil_div(n * 32, 256), 256, 0, s>>>((const float*)ws, n_slices, (int)n, d_bias);
     TIPB_CHECK_LAUNCH("relu_grad_colsum");
     return TIPB_OK;
 }

@@ -13,7 +13,9 @@
 // To keep that scatter free of floating-point atomics the 2T pair-ends of a tile of T pairs are grouped by node
 // inside the CTA (stable counting sort: per-warp ballot ranking, prefix over warps, scan over nodes -- input order
 // inside a group, so every sum has ONE fixed order), and each (node, float4-column) accumulator is owned by one
-// thread for the whole work item.  A work item is a chunk of <= PAIR_CHUNK pairs of ONE relation (host-built table,
+// thread for the whole work item: the Q = dim/4 lanes of a lane group share a node (one float4 column each), so a group's
+// row gather is one contiguous 16*Q-byte read, the index / gradient loads are broadcasts inside the group, and a warp's
+// trip count is the longest list among 32/Q nodes, not among 32.  A work item is a chunk of <= PAIR_CHUNK pairs of ONE relation (host-built table,
 // largest first); it writes  wacc[slot] = w_r * acc  (N x dim),  zacc[slot] = sum_n z[n] * acc[n]  (dim) and its loss
 // partial; slots are numbered relation-major, so the reductions that follow are plain fixed-order sums.
 //
@@ -86,7 +88,10 @@ k_pair_pass(const uint32_t* __restrict__ pos_pairs, const uint32_t* __restrict__
     for (int i = tid; i < n_hi * Q; i += PP_THREADS) acc2[i] = f4_zero();
     if (tid < Q) s_w[tid] = w[size_t(rel) * Q + tid];
 
-    // thread t owns the accumulator row of node t (registers) and of node t + THREADS (shared memory, NPT == 2)
+    // accumulator units: unit u = k * THREADS + tid is (node u / Q, float4 column u % Q = tid % Q); a thread owns up to
+    // Q * NPT units: the first Q in registers, the rest (nodes >= THREADS) in shared memory (acc2, same unit order)
+    constexpr int GROUP_NODES = PP_THREADS / Q;          // nodes covered by one round of units
+    const int myq = tid % Q, mynode0 = tid / Q;
     float4 acc[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) acc[q] = f4_zero();
@@ -215,73 +220,45 @@ k_pair_pass(const uint32_t* __restrict__ pos_pairs, const uint32_t* __restrict__
         }
         __syncthreads();
 
-        // ---- phase 2: every node's accumulator row adds its group, in list order (one thread per node: a full row
-        // per entry costs 2 index loads + Q row loads for 2 Q packed FMAs)
-        if (tid < n_nodes) {
-            const int end = lstart[tid + 1];
-            for (int idx = lstart[tid]; idx < end; ++idx) {
-                const uint32_t en = lists[idx];
-                const float g = gb[en & 0xffffu];
-                const int o = int(en >> 16);
+        // ---- phase 2: every (node, column) unit adds its node's group, in list order.  The Q lanes of a group read the
+        // same list entry / gradient (broadcast) and the Q consecutive float4 of one row (one contiguous read)
 #pragma unroll
-                for (int q = 0; q < Q; ++q) acc[q] = f4_fma(g, zs[zswz<Q>(o, q)], acc[q]);
+        for (int k = 0; k < Q * NPT; ++k) {
+            const int n = k * GROUP_NODES + mynode0;
+            if (n < n_nodes) {
+                float4 a = k < Q ? acc[k < Q ? k : 0] : acc2[(k - Q) * PP_THREADS + tid];
+                const int end = lstart[n + 1];
+                for (int idx = lstart[n]; idx < end; ++idx) {
+                    const uint32_t en = lists[idx];
+                    a = f4_fma(gb[en & 0xffffu], zs[zswz<Q>(int(en >> 16), myq)], a);
+                }
+                if (k < Q) acc[k < Q ? k : 0] = a; else acc2[(k - Q) * PP_THREADS + tid] = a;
             }
-        }
-        if (NPT > 1 && tid < n_hi) {
-            const int n = tid + PP_THREADS;
-            float4 a[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) a[q] = acc2[tid * Q + q];
-            const int end = lstart[n + 1];
-            for (int idx = lstart[n]; idx < end; ++idx) {
-                const uint32_t en = lists[idx];
-                const float g = gb[en & 0xffffu];
-                const int o = int(en >> 16);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) a[q] = f4_fma(g, zs[zswz<Q>(o, q)], a[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) acc2[tid * Q + q] = a[q];
         }
     }
 
     // ---- item epilogue: wacc[slot] = w_r * acc, zacc[slot] = sum_n z[n] * acc[n], loss partial (fixed orders)
-    float4 zsum[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) zsum[q] = f4_zero();
+    float4 zsum = f4_zero();                   // this thread's column (myq) of sum_n z[n] * acc[n]
     float4* wout = wacc + size_t(slot) * n_nodes * Q;
-    if (tid < n_nodes) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            wout[tid * Q + q] = f4_mul(acc[q], s_w[q]);
-            zsum[q] = f4_mul(acc[q], zs[zswz<Q>(tid, q)]);
-        }
-    }
-    if (NPT > 1 && tid < n_hi) {               // (this thread's own rows: no barrier needed)
-        const int n = tid + PP_THREADS;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const float4 a = acc2[tid * Q + q];
-            wout[n * Q + q] = f4_mul(a, s_w[q]);
-            zsum[q] = f4_add(zsum[q], f4_mul(a, zs[zswz<Q>(n, q)]));
+    for (int k = 0; k < Q * NPT; ++k) {        // (this thread's own units: no barrier needed)
+        const int n = k * GROUP_NODES + mynode0;
+        if (n < n_nodes) {
+            const float4 a = k < Q ? acc[k < Q ? k : 0] : acc2[(k - Q) * PP_THREADS + tid];
+            wout[n * Q + myq] = f4_mul(a, s_w[myq]);
+            zsum = f4_add(zsum, f4_mul(a, zs[zswz<Q>(n, myq)]));
         }
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            zsum[q].x += __shfl_xor_sync(FULL, zsum[q].x, o);
-            zsum[q].y += __shfl_xor_sync(FULL, zsum[q].y, o);
-            zsum[q].z += __shfl_xor_sync(FULL, zsum[q].z, o);
-            zsum[q].w += __shfl_xor_sync(FULL, zsum[q].w, o);
-        }
+    for (int o = 16; o >= Q; o >>= 1) {        // lanes with the same lane % Q hold the same column
+        zsum.x += __shfl_xor_sync(FULL, zsum.x, o);
+        zsum.y += __shfl_xor_sync(FULL, zsum.y, o);
+        zsum.z += __shfl_xor_sync(FULL, zsum.z, o);
+        zsum.w += __shfl_xor_sync(FULL, zsum.w, o);
     }
     loss = warp_sum(loss);
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < Q; ++q) s_zacc[wid][q] = zsum[q];
-        s_loss[wid] = loss;
-    }
+    if (lane < Q) s_zacc[wid][lane] = zsum;    // lane % Q == lane here
+    if (lane == 0) s_loss[wid] = loss;
     __syncthreads();
     if (tid < Q) {
         float4 t = s_zacc[0][tid];

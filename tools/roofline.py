@@ -11,9 +11,9 @@ import re
 # sum_l, sum_w (sampler window sizes), F0/F1/F2 (R-GCN widths), dim (decoder width)
 
 FAMILIES = [
-    ("P-P GCN + hierarchy", r"k_node_aggregate|k_hier_|k_gcn_|k_lin_"),
+    ("P-P GCN + hierarchy", r"k_node_aggregate|k_hier_|k_gcn_|k_lin_|k_gemm|k_transpose|k_mask_colsum|k_colsum_finish|k_drug_input"),
     ("R-GCN layer 1 fwd", None), ("R-GCN layer 2 fwd", None), ("R-GCN layer 2 bwd", None), ("R-GCN layer 1 bwd", None),
-    ("decoder + loss (pos+neg, fwd+bwd)", r"k_pair_|k_decoder_|k_loss_reduce|k_add_inplace"),
+    ("decoder + loss (pos+neg, fwd+bwd)", r"k_pair_|k_decoder_|k_loss_reduce|k_add_inplace|k_scale2"),
     ("negative sampler", r"k_accept_count|k_compact|k_window_scan|k_chain_|k_materialize|k_finalize|k_mt_"),
     ("negative plan build", r"k_grp_|k_csr_|k_rel_order|k_scan_lookback|k_sort_"),
     ("Adam", r"k_adam"),
