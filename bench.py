@@ -320,7 +320,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120), pg_options=opts)
     from tip_b200 import layers, neg_sampling as ns
 
     data, workload = make_data(args.shape, args.mod)
@@ -378,7 +379,10 @@ def run_b200_arm(args):
             model.embeddings = None          # drop the last eager autograd graph before capturing
             opt.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # sharded runs: the main chain (P-P encoder, R-GCN, collectives) is captured on a high-priority stream, the
+            # sampler's side stream has the default priority (tip_b200/parallel.py)
+            cap = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+            with torch.cuda.graph(graph, stream=cap):
                 static_loss = step().detach()
             for _ in range(2):
                 graph.replay()

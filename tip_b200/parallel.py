@@ -108,7 +108,7 @@ class _ShardedRGCN(torch.autograd.Function):
     the partial d(x), d(basis), d(root) travel in ONE packed all-reduce, d(att) stays local (own relations)."""
 
     @staticmethod
-    def forward(ctx, x, basis, att_local, root, plan_dst, plan_src, coll, inv_world):
+    def forward(ctx, x, basis, att_local, root, plan_dst, plan_src, coll, add_root, zero_root):
         x, basis, att_local, root = (t.contiguous() for t in (x, basis, att_local, root))
         n, f_in = x.shape
         n_bases, _, f_out = basis.shape
@@ -116,39 +116,40 @@ class _ShardedRGCN(torch.autograd.Function):
         L = lib()
         out = torch.empty((n, f_out), dtype=torch.float32, device=x.device)
         g_saved = torch.empty((n, n_bases, f_in), dtype=torch.float32, device=x.device)
-        root_share = root * inv_world            # every rank adds x @ root / world: the sum adds it once
+        # x @ root belongs to the sum once: rank 0 adds it, the other ranks pass a zero matrix (no scaling kernels)
+        root_eff = root if add_root else zero_root
         ws = ops.workspace(L.tipb_rgcn_workspace_bytes(plan_dst.n_entries, n, n_rel, f_in, f_out, n_bases), x.device)
         check(L.tipb_rgcn_fwd(ptr(plan_dst.buf), plan_dst.n_entries, n, n_rel, ptr(x), ptr(basis), ptr(att_local),
-                              ptr(root_share), None, f_in, f_out, n_bases, 0, ptr(out), ptr(g_saved), ptr(ws), ws.numel(),
+                              ptr(root_eff), None, f_in, f_out, n_bases, 0, ptr(out), ptr(g_saved), ptr(ws), ws.numel(),
                               stream()), "rgcn_fwd")
         coll.all_reduce_(out)
-        ctx.save_for_backward(x, basis, att_local, root_share, g_saved)
-        ctx.plan_dst, ctx.plan_src, ctx.coll, ctx.inv_world = plan_dst, plan_src, coll, inv_world
+        ctx.save_for_backward(x, basis, att_local, root_eff, g_saved)
+        ctx.plan_dst, ctx.plan_src, ctx.coll = plan_dst, plan_src, coll
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, basis, att_local, root_share, g_saved = ctx.saved_tensors
+        x, basis, att_local, root_eff, g_saved = ctx.saved_tensors
         plan_dst, plan_src = ctx.plan_dst, ctx.plan_src
         grad_out = grad_out.contiguous()
         n, f_in = x.shape
         n_bases, _, f_out = basis.shape
         n_rel = att_local.shape[0]
         L = lib()
-        # d_x | d_basis | d_root in one buffer: one all-reduce
-        sizes = (x.numel(), basis.numel(), root_share.numel())
+        # d_x | d_basis in one buffer: one all-reduce.  d_root = X^T g does not depend on the shard (x and g are
+        # replicated): every rank computes it in full, it does not travel
+        sizes = (x.numel(), basis.numel())
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
-        d_x, d_basis, d_root = (t.view(s) for t, s in zip(flat.split(sizes), (x.shape, basis.shape, root_share.shape)))
-        d_att = torch.empty_like(att_local)
+        d_x, d_basis = (t.view(s) for t, s in zip(flat.split(sizes), (x.shape, basis.shape)))
+        d_att, d_root = torch.empty_like(att_local), torch.empty_like(root_eff)
         ws = ops.workspace(L.tipb_rgcn_workspace_bytes(plan_src.n_entries, n, n_rel, f_in, f_out, n_bases), x.device)
         check(L.tipb_rgcn_bwd(ptr(plan_src.buf), plan_src.n_entries, n, n_rel, ptr(plan_dst.inv_deg), ptr(x), ptr(basis),
-                              ptr(att_local), ptr(root_share), ptr(g_saved), ptr(grad_out), None, f_in, f_out, n_bases,
+                              ptr(att_local), ptr(root_eff), ptr(g_saved), ptr(grad_out), None, f_in, f_out, n_bases,
                               ptr(d_x), ptr(d_basis), ptr(d_att), ptr(d_root), None, ptr(ws), ws.numel(), stream()),
               "rgcn_bwd")
-        d_root.mul_(ctx.inv_world)               # chain rule of root_share = root / world (sums to X^T g over the ranks)
-        # the x @ root / world term also sent g @ root^T / world into d_x on every rank: the sum restores it once
+        # (the g @ root^T term of d_x is present on rank 0 only, like x @ root in forward: the sum holds it once)
         ctx.coll.all_reduce_(flat)
-        return d_x, d_basis, d_att, d_root, None, None, None, None
+        return d_x, d_basis, d_att, d_root, None, None, None, None, None
 
 
 class ShardedTIP(TIP):
@@ -164,6 +165,7 @@ class ShardedTIP(TIP):
         object.__setattr__(self, "world", int(world))
         object.__setattr__(self, "coll", collective if collective is not None else _Collective(world))
         object.__setattr__(self, "defer_loss_reduce", bool(defer_loss_reduce))
+        object.__setattr__(self, "_zero_roots", {})
         super().__init__(settings, device, mod=mod, data_path=data_path, data=data)
 
     # ---- data: the base class moved everything to the device; derive this rank's shard
@@ -265,7 +267,10 @@ class ShardedTIP(TIP):
     # ---- encoder
     def _rgcn_local(self, conv, x, relu):
         att = conv.att[self.r_lo:self.r_hi] if self.n_local_rel else conv.att[:1] * 0.0
-        out = _ShardedRGCN.apply(x, conv.basis, att, conv.root, self.plan_dst, self.plan_src, self.coll, 1.0 / self.world)
+        zero = self._zero_roots.get(id(conv))
+        if zero is None:
+            zero = self._zero_roots[id(conv)] = torch.zeros_like(conv.root)
+        out = _ShardedRGCN.apply(x, conv.basis, att, conv.root, self.plan_dst, self.plan_src, self.coll, self.rank == 0, zero)
         return torch.relu(out) if relu else out
 
     def _drug_input(self):
@@ -281,7 +286,9 @@ class ShardedTIP(TIP):
     def forward(self, check_status=True):
         d = self.data
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            # one rank's share of the encoder is short: with more than one rank the main chain (replicated P-P encoder,
+            # collectives) is the critical one and the sampler must not take its SM slots
+            self._side = torch.cuda.Stream(device=self.device, priority=-1 if self.world == 1 else 0)
         cur = torch.cuda.current_stream(self.device)
         from . import layers as _layers
         side = cur if _layers.SERIAL_STREAMS else self._side
