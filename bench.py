@@ -42,6 +42,9 @@ def parse():
                     help="scaled = BASELINE.json config 4 (10k drugs, 100k proteins, 4k relations, ~50M directed D-D edges)")
     ap.add_argument("--model", default="tip", choices=["tip", "dd"],
                     help="dd = BASELINE.json config 3: the D-D-only R-GCN of test/dd_net_scalable.py, relation-sharded")
+    ap.add_argument("--workload", default="train", choices=["train", "sweep"],
+                    help="sweep = BASELINE.json config 5: the decoder-only inference sweep, all 645^2 drug pairs x 861 "
+                         "relations (a step = one full prediction tensor through the C ABI)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--cpu-sample-relations", type=int, default=160,
                     help="relations of the workload the CPU reference arm runs per step (its autograd backward costs "
@@ -515,8 +518,86 @@ def measure_e2e(model, opt, data, steps, e_total, world=1, sharded=False):
                     "between barriers, max over ranks; bytes summed over ranks"}
 
 
+def run_sweep(args):
+    """BASELINE.json config 5: the full prediction tensor [861, 645, 645] (1.43 GB of fp32 scores) per step, through
+    tipb_decoder_sweep on a preallocated output; L2 flushed between steps; roofline = the DRAM write stream."""
+    from tip_b200 import _lib
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                   # one relation-independent kernel: replicas only, rank 0 reports
+    torch.manual_seed(0)
+    n, r, dim = 645, 861, 16
+    z = torch.randn(n, dim, device=dev)
+    w = torch.randn(r, dim, device=dev) * 0.25
+    z_host, w_host = z.cpu().pin_memory(), w.cpu().pin_memory()
+    out = torch.empty((r, n, n), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+
+    def step():
+        _lib.check(L.tipb_decoder_sweep(z.data_ptr(), w.data_ptr(), n, r, dim, 1, out.data_ptr(), _lib.stream()), "decoder_sweep")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    total = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1) * 1e-3
+    clock_info = clocks.stop()
+    assert L.tipb_decoder_sweep_status() == 0
+    t = total / args.steps
+    # end to end: embeddings and relation weights from pinned host memory, one score row block read back
+    probe = torch.empty(n, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        z.copy_(z_host, non_blocking=True)
+        w.copy_(w_host, non_blocking=True)
+        step()
+        probe.copy_(out[r - 1, n - 1], non_blocking=True)
+        torch.cuda.synchronize()
+    te = (time.perf_counter() - t0) / args.steps
+    rel = torch.tensor([0, 17, 430, 860], device=dev)
+    ref = torch.sigmoid(torch.einsum("ik,rk,jk->rij", z.double(), w[rel].double(), z.double()))
+    err = float((out[rel].double() - ref).abs().max())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    nbytes = out.numel() * 4
+    line = {"metric": "decoder_sweep_scores_per_s", "value": out.numel() / t, "unit": "scores/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (three bf16 pieces per operand on tcgen05, fp32 accumulation)",
+            "data": "synthetic", "config": {"workload": "decoder-only inference sweep: all 645^2 drug pairs x 861 relations "
+                                            "(BASELINE.json config 5)", "scores": out.numel(), "l2": "256 MB flush between steps"},
+            "clocks": clock_info,
+            "roofline": {"bound": "hbm", "kernel": "k_decoder_sweep_tc<16>", "achieved": nbytes / t / 1e9, "peak": peak,
+                         "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6.65 TB/s", "unit": "GB/s",
+                         "frac": nbytes / t / 1e9 / peak, "algorithmic_bytes": nbytes, "formula": "4 B per score written",
+                         "traffic": None},
+            "cpu_baseline": None,
+            "e2e": {"value": out.numel() / te, "unit": "scores/s", "h2d_bytes_per_step": (z.numel() + w.numel()) * 4,
+                    "d2h_bytes_per_step": n * 4, "ms_per_step": te * 1e3},
+            "gpu_launches": args.steps, "gpu_launches_per_step": 1, "max_abs_err_vs_float64": err}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "sweep" and args.impl != "reference":
+        run_sweep(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -105,6 +105,9 @@ int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, i
                   const float* basis, const float* att, const float* root, const float* bias /* or NULL */,
                   int f_in, int f_out, int n_bases, int relu_out, float* out, float* g_saved, void* ws,
                   size_t ws_bytes, void* stream);
+/* The node contraction G_i = att_i^T H_i of the forward pass runs on tcgen05 (csrc/rgcn_tc.cuh) for f_in in {32, 64} and
+ * n_bases in {16, 32}; its barrier waits are bounded: 0 = no protocol fault so far (one blocking device read). */
+int tipb_rgcn_tc_status(void);
 int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, int64_t n_rel,
                   const float* inv_deg_dst /* TIPB_CSR_INV_DEG of the by-dst plan */, const float* x,
                   const float* basis, const float* att, const float* root, const float* g_saved,

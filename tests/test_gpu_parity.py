@@ -596,7 +596,8 @@ def _random_typed_graph(rng, n, r, e):
     return ei, et, rl
 
 
-@pytest.mark.parametrize("shape", [(645, 200, 300_000, 64, 32, 32), (333, 50, 40_000, 32, 16, 32), (97, 7, 3000, 20, 6, 3)])
+@pytest.mark.parametrize("shape", [(645, 200, 300_000, 64, 32, 32), (333, 50, 40_000, 32, 16, 32), (97, 7, 3000, 20, 6, 3),
+                                   (300, 400, 200_000, 64, 32, 32), (200, 300, 60_000, 32, 16, 16)])   # >= 256 relations: tcgen05 node kernels
 def test_rgcn_against_fp64_oracle(shape):
     from oracle import tip_oracle as to
     from tip_b200 import layers
@@ -622,6 +623,8 @@ def test_rgcn_against_fp64_oracle(shape):
     # fused ReLU epilogue == relu(conv)
     out_r = conv(xg.detach(), T(ei, d), T(et, d), T(rl, d), _fused_relu=True)
     assert torch.equal(out_r, torch.relu(out.detach()))
+    from tip_b200._lib import lib
+    assert lib().tipb_rgcn_tc_status() == 0       # the tcgen05 node kernels completed their barrier protocol
 
 
 def test_bce_loss_against_oracle():

@@ -29,6 +29,7 @@ SIGNATURES = {
     "tipb_seg_aggregate": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i32, _p, _p]),
     "tipb_rgcn_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i32]),
     "tipb_rgcn_fwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tipb_rgcn_tc_status": (C.c_int, []),
     "tipb_rgcn_bwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32,
                                 _p, _p, _p, _p, _p, _p, _sz, _p]),
     "tipb_gcn_norm": (C.c_int, [_p, _i64, _i64, _p, _p]),

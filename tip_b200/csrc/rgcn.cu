@@ -20,6 +20,8 @@
 #include "seg_aggregate.cuh"
 #include "reduce.cuh"
 #include "rgcn_tiled.cuh"
+#include "rgcn_tc.cuh"
+#include "rgcn_dense.cuh"
 
 namespace tipb {
 
@@ -394,10 +396,24 @@ static int check_dims(const char* who, int f_in, int f_out, int n_bases) {
 struct FwdWs { float* H; };
 struct BwdWs { float *T, *datt_seg, *geff, *ghat, *partial; };
 
-static size_t fwd_ws_bytes(int64_t seg_cap, int f_in) { return size_t(seg_cap) * f_in * 4 + 512; }
+static size_t fwd_ws_bytes(int64_t seg_cap, int64_t n_nodes, int f_in, int f_out) {
+    return (size_t(seg_cap) * f_in + rgcn_dense_fwd_ws_floats(n_nodes, f_out)) * 4 + 1024;
+}
 static size_t bwd_ws_bytes(int64_t seg_cap, int64_t n_nodes, int f_in, int f_out, int n_bases) {
     size_t m = size_t(n_bases) * f_in > size_t(f_in) ? size_t(n_bases) * f_in : size_t(f_in);
-    return (size_t(seg_cap) * (f_out + n_bases) + 2 * size_t(n_nodes) * f_out + atb_ws_floats((int)m, f_out)) * 4 + 2048;
+    return (size_t(seg_cap) * (f_out + n_bases) + 2 * size_t(n_nodes) * f_out + atb_ws_floats((int)m, f_out) +
+            rgcn_dense_bwd_ws_floats(n_nodes, f_in, f_out, n_bases)) * 4 + 4096;
+}
+
+constexpr int64_t RGCN_TC_MIN_REL = 256;     // relations (= upper bound of a node's segments) from which tcgen05 pays off
+static int rgcn_tc_dbg() {
+    static const int v = [] { const char* e = getenv("TIPB_RGCN_TC_DBG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+int* rgcn_tc_error_flag() {
+    static int* ptr = nullptr;
+    if (!ptr) cudaGetSymbolAddress(reinterpret_cast<void**>(&ptr), g_rgcn_tc_error);
+    return ptr;
 }
 
 }  // namespace tipb
@@ -417,8 +433,15 @@ size_t tipb_rgcn_workspace_bytes(int64_t n_entries, int64_t n_nodes, int64_t n_r
     int64_t cap = n_nodes * n_rel;
     int64_t seg_cap = n_entries < cap ? n_entries : cap;
     if (seg_cap < 1) seg_cap = 1;
-    size_t a = fwd_ws_bytes(seg_cap, f_in), b = bwd_ws_bytes(seg_cap, n_nodes, f_in, f_out, n_bases);
+    size_t a = fwd_ws_bytes(seg_cap, n_nodes, f_in, f_out), b = bwd_ws_bytes(seg_cap, n_nodes, f_in, f_out, n_bases);
     return a > b ? a : b;
+}
+
+// 0 = every tensor-core node kernel so far completed its barrier protocol (one blocking device read)
+int tipb_rgcn_tc_status(void) {
+    int v = 0;
+    if (cudaMemcpy(&v, rgcn_tc_error_flag(), sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
 }
 
 int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, int64_t n_rel, const float* x,
@@ -428,11 +451,40 @@ int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, i
     if (rc) return rc;
     TIPB_CHECK_ARG(plan_by_dst && x && basis && att && root && out && g_saved && ws, "rgcn_fwd: NULL argument");
     CsrView v = csr_view(plan_by_dst, n_entries, n_nodes, n_rel);
-    TIPB_CHECK_ARG(ws_bytes >= fwd_ws_bytes(v.seg_cap, f_in), "rgcn_fwd: workspace too small");
+    TIPB_CHECK_ARG(ws_bytes >= fwd_ws_bytes(v.seg_cap, n_nodes, f_in, f_out), "rgcn_fwd: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     Carver c(ws);
     float* H = c.take<float>(size_t(v.seg_cap) * f_in);
+    float* out_partial = c.take<float>(rgcn_dense_fwd_ws_floats(n_nodes, f_out));
     if ((rc = seg_aggregate_launch(v, x, nullptr, nullptr, (int)n_nodes, f_in, H, s))) return rc;
+
+    // tensor-core node contraction (rgcn_tc.cuh) for the shapes of the TIP / D-D nets; TIPB_RGCN_TC=0 selects the
+    // CUDA-core kernels below (measurements, and the shapes the tcgen05 form does not cover)
+    // (a node of a relation shard has few segments -- 861 / 8 relations on 8 GPUs: the per-node set-up of the tcgen05
+    // kernel then outweighs its main loop, and the tiled kernel with its five CTAs per SM is the faster one)
+    static const bool tc_env = [] { const char* e = getenv("TIPB_RGCN_TC"); return !(e && e[0] == '0'); }();
+    const bool use_tc = tc_env && n_rel >= RGCN_TC_MIN_REL;
+#define TC_FWD(FV, NBV)                                                                                            \
+    {                                                                                                              \
+        auto kern = k_rgcn_node_fwd_tc<FV, NBV>;                                                                   \
+        const size_t sm = RtLayout<FV, NBV>::BYTES;                                                                \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, H, att, g_saved, rgcn_tc_error_flag(), \
+                                                       rgcn_tc_dbg());                                             \
+        TIPB_CHECK_LAUNCH("rgcn_node_fwd_tc");                                                                     \
+        return basis_out_launch(g_saved, basis, v.inv_deg, x, root, bias, (int)n_nodes, f_in, f_out, n_bases,      \
+                                relu_out, out_partial, out, s);                                                    \
+    }
+    if (use_tc && (f_out == 16 || f_out == 32 || f_out == 64 || f_out == 128)) {
+        if (n_bases == 32) {
+            if (f_in == 64) TC_FWD(64, 32)
+            if (f_in == 32) TC_FWD(32, 32)
+        } else if (n_bases == 16) {
+            if (f_in == 64) TC_FWD(64, 16)
+            if (f_in == 32) TC_FWD(32, 16)
+        }
+    }
+#undef TC_FWD
 
     // register-tiled kernel for the common shapes
 #define TILED_FWD(TFV, NBQV)                                                                                       \
@@ -499,6 +551,9 @@ int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, i
     float* ghat = c.take<float>(size_t(n_nodes) * f_out);
     const int m_basis = n_bases * f_in;
     float* partial = c.take<float>(atb_ws_floats(m_basis > f_in ? m_basis : f_in, f_out));
+    float* Ybuf = c.take<float>(size_t(n_nodes) * n_bases * f_out);
+    float* Qbuf = c.take<float>(size_t(n_nodes) * n_bases * f_out);
+    float* dx_partial = c.take<float>(size_t(RD_DX_SLICES + 1) * n_nodes * f_in);
 
     k_rgcn_grad_prep<<<(unsigned)ceil_div(n_nodes * f_out, 256), 256, 0, s>>>(grad_out, out_for_relu, inv_deg_dst, n_nodes,
                                                                               f_out, geff, ghat);
@@ -525,7 +580,29 @@ int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, i
                                                           datt_seg, d_x);                                          \
         tiled = true;                                                                                              \
     }
-    if (n_bases == 32) {
+    static const bool tc_env = [] { const char* e = getenv("TIPB_RGCN_TC"); return !(e && (e[0] == '0' || e[0] == '1')); }();
+    const bool use_tc = tc_env && n_rel >= RGCN_TC_MIN_REL;
+#define TC_BWD(FOV, NBV)                                                                                           \
+    {                                                                                                              \
+        if ((rc = basis_y_launch(x, basis, (int)n_nodes, f_in, f_out, n_bases, Ybuf, s))) return rc;               \
+        auto kern = k_rgcn_node_bwd_tc<FOV, NBV>;                                                                  \
+        const size_t sm = RtBwdLayout<FOV, NBV>::BYTES;                                                            \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, T, att, Ybuf, datt_seg, Qbuf,        \
+                                                       rgcn_tc_error_flag(), rgcn_tc_dbg());                       \
+        if ((rc = basis_dx_launch(Qbuf, basis, geff, root, (int)n_nodes, f_in, f_out, n_bases, dx_partial, d_x, s))) return rc; \
+        tiled = true;                                                                                              \
+    }
+    if (use_tc && (f_in == 16 || f_in == 32 || f_in == 64 || f_in == 128)) {      // TIPB_RGCN_TC=1: forward pass only
+        if (n_bases == 32) {
+            if (f_out == 32) TC_BWD(32, 32) else if (f_out == 16) TC_BWD(16, 32)
+        } else if (n_bases == 16) {
+            if (f_out == 32) TC_BWD(32, 16) else if (f_out == 16) TC_BWD(16, 16)
+        }
+    }
+#undef TC_BWD
+    if (tiled) {
+    } else if (n_bases == 32) {
         if (f_out == 64) TILED_BWD(16, 8) else if (f_out == 32) TILED_BWD(8, 8) else if (f_out == 16) TILED_BWD(4, 8)
     } else if (n_bases == 16) {
         if (f_out == 64) TILED_BWD(16, 4) else if (f_out == 32) TILED_BWD(8, 4) else if (f_out == 16) TILED_BWD(4, 4)

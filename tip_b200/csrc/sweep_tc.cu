@@ -29,9 +29,7 @@
 // 931 us for the CUDA-core kernel; MMAs + handshakes alone 59 us, + TMEM loads 69 us, + sigmoid and staging 242 us:
 // the rest is the store loop (two partial lines per 512-byte row segment).  Bits 1..6 of `apply_sigmoid` switch parts of
 // the epilogue off -- they exist for exactly these measurements and are not part of the ABI contract.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace tipb {
 
@@ -43,103 +41,6 @@ constexpr int ST_TILE_N = 256;           // rows c per N-tile = MMA N = TMEM col
 constexpr int ST_TILE_M = 128;           // rows j per M-tile = MMA M = TMEM lanes
 constexpr int ST_MAX_MTILES = 6;         // n_nodes <= 768
 constexpr int ST_CH_PER_WARP = ST_TILE_N / 32 / ST_GROUPS;     // 32-column chunks of an accumulator per warp: 2
-constexpr uint32_t ST_SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug becomes an error flag, not a hang
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// returns false on timeout
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (uint32_t spin = 0; spin < ST_SPIN_LIMIT; ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return true;
-    }
-    return false;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> f32, one K = 16 step
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 bytes
-// stored contiguously (128 B); LBO = byte distance between the two core matrices of one K = 16 step, SBO = byte
-// distance between 8-row groups; version 1 (sm_100), layout type 0 (no swizzle)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= uint64_t((smem_addr >> 4) & 0x3fffu);
-    d |= uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= uint64_t(1) << 46;
-    return d;
-}
-// cute::UMMA::InstrDescriptor for kind::f16: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
-// N >> 3 at bits [17,23), M >> 4 at bits [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
-}
-
-// the three bf16 pieces of 8 consecutive floats -> three 16-byte chunks (8 bf16 each)
-struct Pieces8 { uint4 hi, mid, lo; };
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&p);
-}
-__device__ __forceinline__ Pieces8 split8(const float (&x)[8]) {
-    float h[8], m[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
-        const float r1 = x[i] - h[i];                     // exact
-        m[i] = __bfloat162float(__float2bfloat16_rn(r1));
-        l[i] = r1 - m[i];                                 // exact; rounded to bf16 when packed
-    }
-    Pieces8 p;
-    p.hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    p.mid = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
-    p.lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
-    return p;
-}
 
 // operand row layout: the three bf16 pieces [hi | mid | lo] of a row side by side, DIM = 16 elements (one K = 16 MMA
 // step) each; the six products pick their pieces through the descriptor start address
