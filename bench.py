@@ -272,6 +272,9 @@ def roofline_block(model, serial_steps, step_s, peaks):
     n = float(len(serial_steps))
     total_us = sum(k["us"] for k in per_kernel.values()) / n
     mine = {k: v for k, v in per_kernel.items() if not k.startswith("(torch)")}
+    if not mine:    # CUPTI is taken (the run is itself under ncu / another profiler): no per-kernel times, no roofline claim
+        return {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                "note": "no CUPTI kernel records (profiler attached): a line printed under a profiler is not a bench value"}
     dom = max(mine, key=lambda k: mine[k]["us"])
     dk = mine[dom]
     launches = dk["launches"] / n

@@ -69,9 +69,19 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
         fence_barrier_init();
     }
     if (wid == 0 && !(dbg & 64)) tmem_alloc(&s_tmem_base, 32);
-    // zero both stages once: rows f >= F of the A tiles are never written and must read as zero
-    if (!(dbg & 128))
-    for (int k = tid; k < 2 * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
+    // rows f >= F of the A tiles are never written and must read as zero: row groups F / 8 .. 7 are one contiguous byte
+    // range of every piece (nothing to do for F = 64); the measurement modes zero everything
+    if (dbg) {
+        if (!(dbg & 128))
+        for (int k = tid; k < 2 * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (F < RT_M) {
+        constexpr int Z16 = (RT_M - F) / 8 * RT_SBO / 16;           // 16-byte words per piece
+        for (int k = tid; k < 6 * Z16; k += RT_THREADS) {
+            const int piece = k / Z16, w = k % Z16;               // piece = stage * 3 + piece index
+            uint8_t* base = stage0 + (piece / 3) * LY::STAGE + (piece % 3) * LY::A_PIECE + (F / 8) * RT_SBO;
+            reinterpret_cast<uint4*>(base)[w] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -86,21 +96,44 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     // two register sets: the loads of chunk c + 2 are issued right after chunk c is converted, so every load has a whole
     // chunk trip (conversion, barrier, MMA hand-off) to land before its values are needed
     float ra0[A_ITERS][8], rb0[8], ra1[A_ITERS][8], rb1[8];
+    // Full chunks (all but a node's last) take unpredicated loads at compile-time offsets from two running pointers; the
+    // first version spent ~7 instructions per load on per-element bounds predicates and 64-bit index arithmetic and was
+    // issue bound at two CTAs per SM.
+    const float* const pa0 = H + int64_t(sb + ao * 8) * F + af;
+    const int* const pr0 = seg_rel + sb + bo * 8;
     auto load_raw = [&](int c, float (&ra)[A_ITERS][8], float (&rb)[8]) {
         const int s0 = sb + c * RT_KC;
+        const float* pa = pa0 + int64_t(c) * (RT_KC * F);
+        const int* pr = pr0 + c * RT_KC;
+        if (s0 + RT_KC <= se) {
+            if (a_live) {
 #pragma unroll
-        for (int u = 0; u < A_ITERS; ++u) {
-            const int oct = ao + u * (RT_THREADS / F);
+                for (int u = 0; u < A_ITERS; ++u)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ra[u][j] = pa[(u * (RT_THREADS / F) * 8 + j) * F];
+            }
+            if (b_live) {
+                int rel[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rel[j] = pr[j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rb[j] = att[rel[j] * NB + bb];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < A_ITERS; ++u) {
+                const int oct = ao + u * (RT_THREADS / F);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int s = s0 + oct * 8 + j;
+                    ra[u][j] = (a_live && s < se) ? pa[(u * (RT_THREADS / F) * 8 + j) * F] : 0.f;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int s = s0 + oct * 8 + j;
-                ra[u][j] = (a_live && s < se) ? H[int64_t(s) * F + af] : 0.f;
+                const int s = s0 + bo * 8 + j;
+                rb[j] = (b_live && s < se) ? att[pr[j] * NB + bb] : 0.f;
             }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int s = s0 + bo * 8 + j;
-            rb[j] = (b_live && s < se) ? att[int64_t(seg_rel[s]) * NB + bb] : 0.f;
         }
     };
     auto store_pieces = [&](uint8_t* st, const float (&ra)[A_ITERS][8], const float (&rb)[8]) {
@@ -231,8 +264,18 @@ k_rgcn_node_bwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
         fence_barrier_init();
     }
     if (wid == 0) tmem_alloc(&s_tmem_base, 128);
-    // zero both stages once: rows o >= FO of the A1 tiles are never written and must read as zero
-    for (int k = tid; k < 2 * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
+    // rows o >= FO of the A1 tiles are never written and must read as zero (one contiguous byte range per piece); every
+    // other operand row is rewritten by each chunk.  The measurement modes zero everything.
+    if (dbg) {
+        for (int k = tid; k < 2 * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        constexpr int Z16 = (RT_M - FO) / 8 * RT_SBO / 16;
+        for (int k = tid; k < 6 * Z16; k += RT_THREADS) {
+            const int piece = k / Z16, w = k % Z16;
+            uint8_t* base = stage0 + (piece / 3) * LY::STAGE + (piece % 3) * LY::A1_PIECE + (FO / 8) * RT_SBO;
+            reinterpret_cast<uint4*>(base)[w] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     // B2 pieces (rows b, K = o) from Y[j] = x_j basis (rgcn_dense.cuh: k_basis_y)
     if (n_chunks > 0 && tid < NB * (FO / 8)) {
         const int b = tid / (FO / 8), oc = tid % (FO / 8);
@@ -257,21 +300,45 @@ k_rgcn_node_bwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     const bool a1_live = a1o < RT_KC / 8 && !(dbg & 32), b_live = bo < RT_KC / 8 && !(dbg & 32), a2_live = a2s < RT_KC && !(dbg & 32);
     const int n_prod = (dbg & 7) ? (dbg & 7) : 6;
     float ra0[8], rb0[8], r20[8], ra1[8], rb1[8], r21[8];     // two register sets, as in the forward kernel
+    // full chunks: unpredicated loads at compile-time offsets from running pointers (see the forward kernel)
+    const float* const pa0 = T + int64_t(sb + a1o * 8) * FO + ao1;
+    const int* const pr0 = seg_rel + sb + bo * 8;
+    const float* const p20 = T + int64_t(sb + a2s) * FO + a2o * 8;
     auto load_raw = [&](int c, float (&ra)[8], float (&rb)[8], float (&r2)[8]) {
         const int s0 = sb + c * RT_KC;
+        const float* pa = pa0 + int64_t(c) * (RT_KC * FO);
+        const int* pr = pr0 + c * RT_KC;
+        const float4* t4 = reinterpret_cast<const float4*>(p20 + int64_t(c) * (RT_KC * FO));
+        if (s0 + RT_KC <= se) {
+            if (a1_live) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int s1 = s0 + a1o * 8 + q, s2 = s0 + bo * 8 + q;
-            ra[q] = (a1_live && s1 < se) ? T[int64_t(s1) * FO + ao1] : 0.f;
-            rb[q] = (b_live && s2 < se) ? att[int64_t(seg_rel[s2]) * NB + bb] : 0.f;
-        }
-        if (a2_live && s0 + a2s < se) {
-            const float4* t4 = reinterpret_cast<const float4*>(T + int64_t(s0 + a2s) * FO + a2o * 8);
-            const float4 u0 = t4[0], u1 = t4[1];
-            r2[0] = u0.x; r2[1] = u0.y; r2[2] = u0.z; r2[3] = u0.w; r2[4] = u1.x; r2[5] = u1.y; r2[6] = u1.z; r2[7] = u1.w;
+                for (int q = 0; q < 8; ++q) ra[q] = pa[q * FO];
+            }
+            if (b_live) {
+                int rel[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rel[q] = pr[q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rb[q] = att[rel[q] * NB + bb];
+            }
+            if (a2_live) {
+                const float4 u0 = t4[0], u1 = t4[1];
+                r2[0] = u0.x; r2[1] = u0.y; r2[2] = u0.z; r2[3] = u0.w; r2[4] = u1.x; r2[5] = u1.y; r2[6] = u1.z; r2[7] = u1.w;
+            }
         } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) r2[q] = 0.f;
+            for (int q = 0; q < 8; ++q) {
+                const int s1 = s0 + a1o * 8 + q, s2 = s0 + bo * 8 + q;
+                ra[q] = (a1_live && s1 < se) ? pa[q * FO] : 0.f;
+                rb[q] = (b_live && s2 < se) ? att[pr[q] * NB + bb] : 0.f;
+            }
+            if (a2_live && s0 + a2s < se) {
+                const float4 u0 = t4[0], u1 = t4[1];
+                r2[0] = u0.x; r2[1] = u0.y; r2[2] = u0.z; r2[3] = u0.w; r2[4] = u1.x; r2[5] = u1.y; r2[6] = u1.z; r2[7] = u1.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r2[q] = 0.f;
+            }
         }
     };
     auto store_pieces = [&](uint8_t* st, const float (&ra)[8], const float (&rb)[8], const float (&r2)[8]) {

@@ -89,19 +89,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&p);
 }
+// two floats -> their three packed bf16x2 pieces (low half = x0).  Only F2FP.BF16.PACK_AB (ALU pipe), shifts/masks and
+// FADDs: the per-value F2F conversions of the first version ran on the 16-lane conversion pipe.  Same roundings, same bits.
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);        // exact
+    mid = pack_bf16x2(r0, r1);
+    const float l0 = r0 - __uint_as_float(mid << 16), l1 = r1 - __uint_as_float(mid & 0xffff0000u);      // exact
+    lo = pack_bf16x2(l0, l1);                                                                           // rounded here
+}
 __device__ __forceinline__ Pieces8 split8(const float (&x)[8]) {
-    float h[8], m[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
-        const float r1 = x[i] - h[i];                     // exact
-        m[i] = __bfloat162float(__float2bfloat16_rn(r1));
-        l[i] = r1 - m[i];                                 // exact; rounded to bf16 when packed
-    }
     Pieces8 p;
-    p.hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    p.mid = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
-    p.lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    split2(x[0], x[1], p.hi.x, p.mid.x, p.lo.x);
+    split2(x[2], x[3], p.hi.y, p.mid.y, p.lo.y);
+    split2(x[4], x[5], p.hi.z, p.mid.z, p.lo.z);
+    split2(x[6], x[7], p.hi.w, p.mid.w, p.lo.w);
     return p;
 }
 

@@ -10,7 +10,7 @@ sys.path.insert(0, __file__.rsplit("/", 2)[0])
 from tools.roofline import short_name  # noqa: E402
 
 raw, out, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
-rows = list(csv.reader(open(raw)))
+rows = list(csv.reader(l for l in open(raw) if l.startswith('"')))   # ncu prefixes ==PROF== lines
 hdr, units = rows[0], rows[1]
 col = {n: i for i, n in enumerate(hdr)}
 scale_b = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

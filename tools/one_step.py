@@ -31,7 +31,7 @@ if os.environ.get("TIPB_DUMP_WORKLOAD"):
     m = ns._membership(d.dd_train_idx, d.n_drug, rl)
     info = dict(E=int(d.dd_train_idx.shape[1]), n_drug=int(d.n_drug), n_prot=int(d.n_prot), n_rel=int(d.n_dd_et),
                 S_dst=int(p_dst.field("counts")[0]), S_src=int(p_src.field("counts")[0]),
-                S_neg=int(model._neg_plan.field("counts")[0]), E_pp=int(d.pp_train_indices.shape[1]),
+                S_neg=int(model._neg_plan.field("counts")[0]) if getattr(model, "_neg_plan", None) is not None else 0, E_pp=int(d.pp_train_indices.shape[1]),
                 E_pd=int(d.dp_edge_index.shape[1]), mt_words=int(624 + ns._get_rng(dev).n_new), sum_l=int(m.sum_l),
                 sum_w=int(m.sum_w))
     json.dump(info, open(os.environ["TIPB_DUMP_WORKLOAD"], "w"))

@@ -64,7 +64,15 @@ class StepModel(object):
         if m and "tiled" in s:
             f = int(m.group(1)) * 4
             return self._rgcn_family(), Ssrc * (4 * f + 8 * B + 12) + N * 8 * f, "S(4F_out+8B+12)+N*8F, F_out=%d" % f
-        if re.match(r"k_rgcn_|k_atb|k_sum_slices|k_rel_reduce", s):
+        m = re.match(r"k_rgcn_node_fwd_tc<(\d+)", s)
+        if m:
+            f = int(m.group(1))
+            return self._rgcn_family(), S * (4 * f + 4 * B + 4) + N * 4 * B * f, "S(4F_in+4B+4)+N*4BF, F_in=%d" % f
+        m = re.match(r"k_rgcn_node_bwd_tc<(\d+)", s)
+        if m:
+            f = int(m.group(1))
+            return self._rgcn_family(), Ssrc * (4 * f + 8 * B + 4) + N * 8 * B * f, "S(4F_out+8B+4)+N*8BF, F_out=%d" % f
+        if re.match(r"k_rgcn_|k_atb|k_sum_slices|k_rel_reduce|k_rd_", s):
             return self._rgcn_family(), None, None
         m = re.match(r"k_pair_pass<(\d+)", s)
         if m:

@@ -20,7 +20,7 @@ E, S, Ssrc, Sneg, R, N = W["E"], W["S_dst"], W["S_src"], W["S_neg"], W["n_rel"],
 Epp, Np, B = W["E_pp"] + W["n_prot"], W["n_prot"], 32
 words = W["mt_words"]
 
-rows = list(csv.reader(open(raw)))
+rows = list(csv.reader(l for l in open(raw) if l.startswith('"')))   # ncu prefixes ==PROF== lines
 hdr = rows[0]
 col = {n: i for i, n in enumerate(hdr)}
 
@@ -74,6 +74,18 @@ def algorithmic(name):
     if m:
         f = int(m.group(1)) * 4
         return Ssrc * (4 * f + 8 * B + 12) + N * 8 * f, "S(4F_out+8B+12)+N*8F, F_out=%d" % f
+    m = re.search(r"k_rgcn_node_fwd_tc<\(?(?:int\))?(\d+)", name)
+    if m:
+        f = int(m.group(1))
+        return S * (4 * f + 4 * B + 4) + N * 4 * B * f, "S(4F_in+4B+4)+N*4BF (G written), F_in=%d" % f
+    m = re.search(r"k_rgcn_node_bwd_tc<\(?(?:int\))?(\d+)", name)
+    if m:
+        f = int(m.group(1))
+        return Ssrc * (4 * f + 8 * B + 4) + N * 8 * B * f, "S(4F_out+4B att+4B d_att+4)+N*8BF (Y read, Q written), F_out=%d" % f
+    m = re.search(r"k_pair_pass<\(?(?:int\))?(\d+)", name)
+    if m:
+        d = int(m.group(1))
+        return 2 * E * (8 + 2 * 4 * d), "2E(8+2*4d), d=%d (pos + neg entries, fwd + gradient fused)" % d
     if "k_grp_place" in name:
         return 2 * E * (16 + 8), "2E(16 read + 8 written)"
     if "k_grp_count" in name:
