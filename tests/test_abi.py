@@ -63,9 +63,10 @@ def test_neg_table_build_is_host_only_and_consistent():
     assert np.array_equal(k, sizes)
     assert lo[0] == 0 and np.all(np.diff(lo) >= 0)
     assert np.all(W >= 1) and np.all((Lw >= W + k) | (k == 0))
-    assert np.array_equal(win_off, np.concatenate([[0], np.cumsum(Lw)[:-1]]))
+    Lp = (Lw + 3) & ~3                                    # window rows start 16-byte aligned (vector stores)
+    assert np.array_equal(win_off, np.concatenate([[0], np.cumsum(Lp)[:-1]])) and np.all(win_off % 4 == 0)
     assert np.array_equal(f_off, np.concatenate([[0], np.cumsum(W)[:-1]]))
-    assert totals[0] == Lw.sum() and totals[1] == W.sum() and totals[2] >= (lo + Lw).max()
+    assert totals[0] == Lp.sum() and totals[1] == W.sum() and totals[2] >= (lo + Lw).max()
     # expected offsets sit inside the brackets: relation r starts near sum(k) + sum(k d/(1-d))
     d = pop / 101.0 ** 2
     mean = np.concatenate([[0], np.cumsum(sizes * d / (1 - d))[:-1]])

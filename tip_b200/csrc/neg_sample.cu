@@ -194,11 +194,16 @@ __device__ __forceinline__ void write_pair(int64_t* __restrict__ out, uint32_t* 
 //   NHI[win_off + x] = number of non-members among window entries 0..x (inclusive)
 //   PR [win_off + m] = window index of the (m+1)-th non-member
 //   F  [f_off + x]   = next relation's start offset if this relation starts at lo + x   (x < W; -1: window too short)
+// STAGED: the relation's bitmap (n_nodes^2 bits; 52 KB for 645 drugs) is copied into shared memory first.  The probes are
+// random 4-byte reads: from global memory each one costs a 32-byte sector and an L1 tag cycle per LANE (the first version
+// ran at ~1 probe per clock per SM: 200 us for 15 M window entries), from shared memory a few bank-conflict replays per warp.
+template <bool STAGED>
 __global__ void __launch_bounds__(1024)
 k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
               int64_t words_per_rel, const int64_t* __restrict__ table, int r_lo, int* __restrict__ NHI,
               int* __restrict__ PR, int* __restrict__ F) {
     // `member` holds the bitmaps of the relations [r_lo, ...) only (a rank's shard; r_lo = 0: all relations)
+    extern __shared__ uint32_t ws_bits[];
     __shared__ int sw[33];
     __shared__ int s_carry;
     const int r = r_lo + blockIdx.x;
@@ -209,17 +214,21 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
         for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = lo + x;
         return;
     }
-    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
+    const uint32_t* gbits = member + int64_t(r - r_lo) * words_per_rel;
     const int n_acc = *n_accepted_ptr;
     if (n_acc <= 0) {  // no usable stream at all
         for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = -1;
         return;
     }
-    int* nhi = NHI + win_off;
+    if (STAGED)
+        for (int i = threadIdx.x; i < int(words_per_rel); i += 1024) ws_bits[i] = gbits[i];
+    const uint32_t* bits = STAGED ? ws_bits : gbits;
+    int* nhi = NHI + win_off;          // win_off is a multiple of 4 (tipb_neg_table_build): 16-byte aligned rows
     int* pr = PR + win_off;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     constexpr int ITEMS = 4;
+    const int L4 = (L + 3) & ~3;       // the padded tail of the row belongs to this relation too
     for (int base = 0; base < L; base += 1024 * ITEMS) {
         const int x0 = base + threadIdx.x * ITEMS;
         int nh[ITEMS];
@@ -261,15 +270,14 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
         }
         __syncthreads();
         int run = s_carry + sw[warp_id()] + incl - local;
+        int cnt[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const int x = x0 + i;
-            if (x < L) {
-                if (nh[i]) pr[run] = x;
-                run += nh[i];
-                nhi[x] = run;
-            }
+            if (nh[i]) pr[run] = x0 + i;            // nh[i] implies x0 + i < L
+            run += nh[i];
+            cnt[i] = run;
         }
+        if (x0 < L4) *reinterpret_cast<int4*>(nhi + x0) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
         __syncthreads();
         if (threadIdx.x == 0) s_carry += sw[32];
         __syncthreads();
@@ -280,6 +288,18 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
         const int target = rb + k;
         F[f_off + x] = target <= total ? lo + pr[target - 1] + 1 : -1;
     }
+}
+
+static int window_scan_launch(const int* A, const int* n_acc, const uint32_t* member, int64_t wpr, const int64_t* table,
+                              int r_lo, int64_t n_rel_local, int* NHI, int* PR, int* F, cudaStream_t s) {
+    const size_t smem = size_t(wpr) * 4;
+    if (smem <= 100 * 1024) {              // two CTAs of 1024 threads per SM still fit
+        if (int rc = ensure_dyn_smem((const void*)k_window_scan<true>, smem)) return rc;
+        k_window_scan<true><<<(unsigned)n_rel_local, 1024, smem, s>>>(A, n_acc, member, wpr, table, r_lo, NHI, PR, F);
+    } else {
+        k_window_scan<false><<<(unsigned)n_rel_local, 1024, 0, s>>>(A, n_acc, member, wpr, table, r_lo, NHI, PR, F);
+    }
+    return TIPB_OK;
 }
 
 // One warp follows o_{r+1} = F_r[o_r - lo_r].  Lane 0 does the dependent lookups out of shared memory: all
@@ -497,13 +517,15 @@ k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ membe
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), k = int(tb[5]);
     const int* nhi = NHI + tb[3];
-    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
     const int i = int(e - start);
     int p = A[o + i];
-    if (is_member(bits, p)) {
-        const int x0 = o - lo;
+    // membership of a window entry is what k_window_scan already decided: entry x is a positive pair iff the
+    // non-member count does not move at x.  Two coalesced loads instead of a random bitmap probe per draw.
+    const int x0 = o - lo, x = x0 + i;
+    const int cur = nhi[x], prev = x == 0 ? 0 : nhi[x - 1];
+    if (cur == prev) {
         const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
-        const int hits_incl = (i + 1) - (nhi[x0 + i] - rb);
+        const int hits_incl = (i + 1) - (cur - rb);
         p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
     }
     write_pair(out, packed, n_edges, e - e_lo, p, n_nodes, float(n_nodes));
@@ -522,7 +544,6 @@ k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ memb
     const int lo = int(tb[0]), k = int(tb[5]);
     if (o < 0 || k == 0) return;
     const int* nhi = NHI + tb[3];
-    const uint32_t* bits = member + int64_t(r - r_lo) * words_per_rel;
     const int64_t start = range_list[2 * r] - e_lo;
     const int x0 = o - lo;
     const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
@@ -536,8 +557,9 @@ k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ memb
         const int xs = s_prev - lo;              // >= 1
         const int nb = nhi[xs - 1];
         for (int p = threadIdx.x; p < c_prev; p += blockDim.x) {
-            if (is_member(bits, A[s_prev + p])) {
-                const int t = (p + 1) - (nhi[xs + p] - nb) - 1;
+            const int cur = nhi[xs + p];
+            if (cur == nhi[xs + p - 1]) {          // a positive pair (xs >= 1): the non-member count did not move
+                const int t = (p + 1) - (cur - nb) - 1;
                 write_pair(out, packed, n_edges, start + p, A[s_cur + t], n_nodes, fn);  // perm[rest] = tmp; rest indexes tmp_{q-1}
             }
         }
@@ -917,7 +939,7 @@ int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount
         int64_t* tb = table_host + r * TAB;
         tb[0] = lo; tb[1] = W; tb[2] = L; tb[3] = sum_l; tb[4] = sum_w; tb[5] = k;
         tb[6] = ksum + int64_t(llround(mean));
-        sum_l += L;
+        sum_l += (L + 3) & ~int64_t(3);       // rows of NHI / PR start 16-byte aligned (vector stores in k_window_scan)
         sum_w += W;
         if (lo + L > max_index) max_index = lo + L;
         if (lo + W > max_index) max_index = lo + W;
@@ -979,7 +1001,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index, neg_packed);
     } else {
-        k_window_scan<<<(unsigned)n_rel, 1024, 0, s>>>(w.A, n_acc, member, wpr, table, 0, w.NHI, w.PR, w.F);
+        if ((rc = window_scan_launch(w.A, n_acc, member, wpr, table, 0, n_rel, w.NHI, w.PR, w.F, s))) return rc;
         const int n_blocks = int(ceil_div(n_rel, CHAIN_BLOCK));
         if (n_blocks <= CHAIN_MAX_BLOCKS && size_t(n_rel) * sizeof(int4) <= 160 * 1024) {
             const size_t tsm = size_t(n_rel) * sizeof(int4);
@@ -1045,7 +1067,7 @@ int tipb_neg_sample_shard_begin(const uint32_t* mt_state, const uint32_t* stream
     const int* n_acc = w.flags + n_chunks;
     const int64_t n_local = r_hi - r_lo;
     if (n_local > 0) {
-        k_window_scan<<<(unsigned)n_local, 1024, 0, s>>>(w.A, n_acc, member_local, wpr, table, (int)r_lo, w.NHI, w.PR, w.F);
+        if ((rc = window_scan_launch(w.A, n_acc, member_local, wpr, table, (int)r_lo, n_local, w.NHI, w.PR, w.F, s))) return rc;
         const int n_blocks = int(ceil_div(n_local, CHAIN_BLOCK));
         k_chain_blocks<<<dim3(16, (unsigned)n_blocks), 256, 0, s>>>(table, w.F, (int)r_lo, (int)r_hi, w.G);
     }
