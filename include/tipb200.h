@@ -183,7 +183,8 @@ int tipb_decoder_sweep_status(void);
  *                 [0,624) = the key block itself, then n_new further words (tipb_mt19937_generate).
  *                 It depends on the state only, so the host may produce it ahead of time.
  *   member        per-relation bitmaps of the positive pairs (+ their popcounts) from tipb_neg_bitmap_build.
- *   table         per-relation brackets of the stream offsets (7 int64 per relation: lo, W, L, win_off, f_off, k, pred)
+ *   table         per-relation brackets of the stream offsets (8 int64 per relation: lo, W, L, win_off, f_off, k, pred, order --
+ *                 row b's `order` = the relation with the b-th longest window, the launch order of the window scan)
  *                 built ON THE HOST from host copies of range_list and the popcounts (tipb_neg_table_build,
  *                 no CUDA call); totals[0..3] = sum_L, sum_W, highest accepted index a window may touch,
  *                 expected accepted values consumed.

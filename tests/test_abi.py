@@ -55,11 +55,12 @@ def test_neg_table_build_is_host_only_and_consistent():
     ends = np.cumsum(sizes)
     rl = np.ascontiguousarray(np.stack([ends - sizes, ends], axis=1))
     pop = np.array([1400, 0, 2300, 40, 8000], dtype=np.int32)
-    table = np.zeros((5, 7), dtype=np.int64)
+    table = np.zeros((5, 8), dtype=np.int64)
     totals = np.zeros(4, dtype=np.int64)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     _lib.check(L.tipb_neg_table_build(vp(rl), vp(pop), 5, 101, 7.0, vp(table), vp(totals)), "table")
-    lo, W, Lw, win_off, f_off, k, pred = table.T
+    lo, W, Lw, win_off, f_off, k, pred, order = table.T
+    assert sorted(order) == list(range(5)) and np.all(np.diff(Lw[order]) <= 0)      # longest window first
     assert np.array_equal(k, sizes)
     assert lo[0] == 0 and np.all(np.diff(lo) >= 0)
     assert np.all(W >= 1) and np.all((Lw >= W + k) | (k == 0))

@@ -30,6 +30,9 @@
 //      the geometrically smaller rounds >= 2 are replayed by one warp per relation (k_materialize_fixup).
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tipb {
@@ -37,7 +40,8 @@ namespace tipb {
 constexpr int MT_N = 624, MT_M = 397, MT_LAG = MT_N - MT_M;  // 227
 constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MATRIX_A = 0x9908b0dfu;
 constexpr int RING = 2048;
-constexpr int TAB = 7;  // per-relation table row: lo, W, L, win_off, f_off, k, pred (expected start offset)
+constexpr int TAB = 8;  // per-relation table row: lo, W, L, win_off, f_off, k, pred (expected start offset), order
+                        // (order: row b holds the relation with the b-th longest window -- launch order of k_window_scan)
 
 enum { NEG_STATUS_OUT_OF_WORDS = 1, NEG_STATUS_TOO_MANY_ROUNDS = 2, NEG_STATUS_BRACKET_MISS = 4 };
 
@@ -197,93 +201,110 @@ __device__ __forceinline__ void write_pair(int64_t* __restrict__ out, uint32_t* 
 // STAGED: the relation's bitmap (n_nodes^2 bits; 52 KB for 645 drugs) is copied into shared memory first.  The probes are
 // random 4-byte reads: from global memory each one costs a 32-byte sector and an L1 tag cycle per LANE (the first version
 // ran at ~1 probe per clock per SM: 200 us for 15 M window entries), from shared memory a few bank-conflict replays per warp.
+//
+// Two passes, ONE block barrier between them (the second version scanned 4096 entries per trip with four barriers each):
+//   pass 1  every warp owns a contiguous run of 32-entry groups: coalesced loads of A, probe, ballot -> the group's
+//           non-member mask (kept in shared memory) and the warp's non-member count;
+//   pass 2  base = sum of the earlier warps' counts; per group, nhi and pr follow from the stored mask alone
+//           (popc of the lanes at or below / below mine): coalesced stores, no second look at A or the bitmap.
+constexpr int WS_THREADS = 1024;
+constexpr int WS_WARPS = WS_THREADS / 32;
+constexpr int WS_MASK_WORDS = 6144;        // group masks kept in shared memory: windows up to 196,608 entries
+
 template <bool STAGED>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(WS_THREADS)
 k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr, const uint32_t* __restrict__ member,
-              int64_t words_per_rel, const int64_t* __restrict__ table, int r_lo, int* __restrict__ NHI,
+              int64_t words_per_rel, const int64_t* __restrict__ table, int r_lo, int by_order, int* __restrict__ NHI,
               int* __restrict__ PR, int* __restrict__ F) {
     // `member` holds the bitmaps of the relations [r_lo, ...) only (a rank's shard; r_lo = 0: all relations)
     extern __shared__ uint32_t ws_bits[];
-    __shared__ int sw[33];
-    __shared__ int s_carry;
-    const int r = r_lo + blockIdx.x;
+    __shared__ uint32_t s_mask[WS_MASK_WORDS];
+    __shared__ int sw[WS_WARPS];
+    // unsharded launches (by_order) take the relations longest window first: the windows differ by 40x and the CTAs
+    // of a launch start in index order, so a long window met late would run alone at the end
+    const int r = by_order ? int(table[int64_t(blockIdx.x) * TAB + 7]) : r_lo + blockIdx.x;
     const int64_t* tb = table + int64_t(r) * TAB;
     const int lo = int(tb[0]), W = int(tb[1]), L = int(tb[2]), k = int(tb[5]);
     const int64_t win_off = tb[3], f_off = tb[4];
     if (k == 0) {
-        for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = lo + x;
+        for (int x = threadIdx.x; x < W; x += WS_THREADS) F[f_off + x] = lo + x;
         return;
     }
     const uint32_t* gbits = member + int64_t(r - r_lo) * words_per_rel;
     const int n_acc = *n_accepted_ptr;
     if (n_acc <= 0) {  // no usable stream at all
-        for (int x = threadIdx.x; x < W; x += 1024) F[f_off + x] = -1;
+        for (int x = threadIdx.x; x < W; x += WS_THREADS) F[f_off + x] = -1;
         return;
     }
-    if (STAGED)
-        for (int i = threadIdx.x; i < int(words_per_rel); i += 1024) ws_bits[i] = gbits[i];
-    const uint32_t* bits = STAGED ? ws_bits : gbits;
-    int* nhi = NHI + win_off;          // win_off is a multiple of 4 (tipb_neg_table_build): 16-byte aligned rows
-    int* pr = PR + win_off;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    constexpr int ITEMS = 4;
-    const int L4 = (L + 3) & ~3;       // the padded tail of the row belongs to this relation too
-    for (int base = 0; base < L; base += 1024 * ITEMS) {
-        const int x0 = base + threadIdx.x * ITEMS;
-        int nh[ITEMS];
-        int local = 0;
-        // unconditional (clamped) loads first, so the four value loads and then the four bitmap probes overlap
-        int val[ITEMS];
-        uint32_t word[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int j = lo + x0 + i;
-            val[i] = A[j < n_acc ? j : max(n_acc - 1, 0)];
-        }
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) word[i] = bits[val[i] >> 5];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int x = x0 + i, j = lo + x;
-            nh[i] = (x < L && j < n_acc && !((word[i] >> (val[i] & 31)) & 1u)) ? 1 : 0;
-            local += nh[i];
-        }
-        // block-wide exclusive scan of `local`
-        int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(FULL, incl, o);
-            if (lane_id() >= o) incl += y;
-        }
-        if (lane_id() == 31) sw[warp_id()] = incl;
-        __syncthreads();
-        if (warp_id() == 0) {
-            int v = sw[lane_id()], xs = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(FULL, xs, o);
-                if (lane_id() >= o) xs += y;
-            }
-            sw[lane_id()] = xs - v;
-            if (lane_id() == 31) sw[32] = xs;
-        }
-        __syncthreads();
-        int run = s_carry + sw[warp_id()] + incl - local;
-        int cnt[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            if (nh[i]) pr[run] = x0 + i;            // nh[i] implies x0 + i < L
-            run += nh[i];
-            cnt[i] = run;
-        }
-        if (x0 < L4) *reinterpret_cast<int4*>(nhi + x0) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += sw[32];
+    if (STAGED) {
+        for (int i = threadIdx.x; i < int(words_per_rel); i += WS_THREADS) ws_bits[i] = gbits[i];
         __syncthreads();
     }
-    const int total = s_carry;
-    for (int x = threadIdx.x; x < W; x += 1024) {
+    const uint32_t* bits = STAGED ? ws_bits : gbits;
+    int* nhi = NHI + win_off;
+    int* pr = PR + win_off;
+    const int lane = lane_id(), wid = warp_id();
+    const int n_groups = (L + 31) >> 5;
+    const int gpw = (n_groups + WS_WARPS - 1) / WS_WARPS;
+    const int g0 = min(wid * gpw, n_groups), g1 = min(g0 + gpw, n_groups);
+    const bool keep = n_groups <= WS_MASK_WORDS;          // uniform over the CTA
+    const int last = n_acc - 1;
+
+    auto group_mask = [&](int g) -> uint32_t {            // non-member mask of group g (all lanes take part)
+        const int x = (g << 5) + lane, j = lo + x;
+        const int v = A[min(j, last)];
+        const bool nm = x < L && j <= last && !((bits[v >> 5] >> (v & 31)) & 1u);
+        return __ballot_sync(FULL, nm);
+    };
+
+    // ---- pass 1
+    int cnt = 0;
+    int g = g0;
+    for (; g + 4 <= g1; g += 4) {                          // four independent load -> probe chains in flight
+        int v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int x = ((g + u) << 5) + lane, j = lo + x;
+            ok[u] = x < L && j <= last;
+            v[u] = A[min(j, last)];
+        }
+        uint32_t wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wd[u] = bits[v[u] >> 5];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t m = __ballot_sync(FULL, ok[u] && !((wd[u] >> (v[u] & 31)) & 1u));
+            if (keep && lane == 0) s_mask[g + u] = m;
+            cnt += __popc(m);
+        }
+    }
+    for (; g < g1; ++g) {
+        const uint32_t m = group_mask(g);
+        if (keep && lane == 0) s_mask[g] = m;
+        cnt += __popc(m);
+    }
+    if (lane == 0) sw[wid] = cnt;
+    __syncthreads();
+    // ---- pass 2: exclusive prefix over the warps, then per group from the masks
+    const int mine = sw[lane];                             // WS_WARPS == 32
+    int run = lane < wid ? mine : 0, total = mine;         // two masked warp sums
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        run += __shfl_xor_sync(FULL, run, o);
+        total += __shfl_xor_sync(FULL, total, o);
+    }
+    const uint32_t le = 0xffffffffu >> (31 - lane), lt = le >> 1;
+    const int L4 = (L + 3) & ~3;                           // the padded tail of the row belongs to this relation too
+    for (g = g0; g < g1; ++g) {
+        const uint32_t m = keep ? s_mask[g] : group_mask(g);
+        const int x = (g << 5) + lane;
+        if ((m >> lane) & 1u) pr[run + __popc(m & lt)] = x;
+        if (x < L4) nhi[x] = run + __popc(m & le);
+        run += __popc(m);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += WS_THREADS) {
         const int rb = x == 0 ? 0 : nhi[x - 1];
         const int target = rb + k;
         F[f_off + x] = target <= total ? lo + pr[target - 1] + 1 : -1;
@@ -291,13 +312,13 @@ k_window_scan(const int* __restrict__ A, const int* __restrict__ n_accepted_ptr,
 }
 
 static int window_scan_launch(const int* A, const int* n_acc, const uint32_t* member, int64_t wpr, const int64_t* table,
-                              int r_lo, int64_t n_rel_local, int* NHI, int* PR, int* F, cudaStream_t s) {
+                              int r_lo, int64_t n_rel_local, int by_order, int* NHI, int* PR, int* F, cudaStream_t s) {
     const size_t smem = size_t(wpr) * 4;
-    if (smem <= 100 * 1024) {              // two CTAs of 1024 threads per SM still fit
+    if (smem <= 84 * 1024) {               // + 24 KB of group masks: two CTAs of 1024 threads per SM still fit
         if (int rc = ensure_dyn_smem((const void*)k_window_scan<true>, smem)) return rc;
-        k_window_scan<true><<<(unsigned)n_rel_local, 1024, smem, s>>>(A, n_acc, member, wpr, table, r_lo, NHI, PR, F);
+        k_window_scan<true><<<(unsigned)n_rel_local, WS_THREADS, smem, s>>>(A, n_acc, member, wpr, table, r_lo, by_order, NHI, PR, F);
     } else {
-        k_window_scan<false><<<(unsigned)n_rel_local, 1024, 0, s>>>(A, n_acc, member, wpr, table, r_lo, NHI, PR, F);
+        k_window_scan<false><<<(unsigned)n_rel_local, WS_THREADS, 0, s>>>(A, n_acc, member, wpr, table, r_lo, by_order, NHI, PR, F);
     }
     return TIPB_OK;
 }
@@ -949,6 +970,12 @@ int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount
     }
     TIPB_CHECK_ARG(max_index < (int64_t(1) << 31) - 4096 && sum_l < (int64_t(1) << 31) && sum_w < (int64_t(1) << 31),
                    "neg_table_build: edge set too large for 32-bit stream offsets");
+    {   // column 7: relations by window length, longest first (stable)
+        std::vector<int64_t> order(static_cast<size_t>(n_rel));
+        for (int64_t r = 0; r < n_rel; ++r) order[size_t(r)] = r;
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return table_host[a * TAB + 2] > table_host[b * TAB + 2]; });
+        for (int64_t b = 0; b < n_rel; ++b) table_host[b * TAB + 7] = order[size_t(b)];
+    }
     totals_host[0] = sum_l;
     totals_host[1] = sum_w;
     totals_host[2] = max_index;                        // accepted values the windows may touch
@@ -1001,7 +1028,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         k_materialize_exact<<<(unsigned)n_rel, 256, 0, s>>>(w.A, member, wpr, range_list, w.rounds, w.round_ptr,
                                                             w.n_rounds, (int)n_nodes, n_edges, w.perm, neg_edge_index, neg_packed);
     } else {
-        if ((rc = window_scan_launch(w.A, n_acc, member, wpr, table, 0, n_rel, w.NHI, w.PR, w.F, s))) return rc;
+        if ((rc = window_scan_launch(w.A, n_acc, member, wpr, table, 0, n_rel, 1, w.NHI, w.PR, w.F, s))) return rc;
         const int n_blocks = int(ceil_div(n_rel, CHAIN_BLOCK));
         if (n_blocks <= CHAIN_MAX_BLOCKS && size_t(n_rel) * sizeof(int4) <= 160 * 1024) {
             const size_t tsm = size_t(n_rel) * sizeof(int4);
@@ -1067,7 +1094,7 @@ int tipb_neg_sample_shard_begin(const uint32_t* mt_state, const uint32_t* stream
     const int* n_acc = w.flags + n_chunks;
     const int64_t n_local = r_hi - r_lo;
     if (n_local > 0) {
-        if ((rc = window_scan_launch(w.A, n_acc, member_local, wpr, table, (int)r_lo, n_local, w.NHI, w.PR, w.F, s))) return rc;
+        if ((rc = window_scan_launch(w.A, n_acc, member_local, wpr, table, (int)r_lo, n_local, 0, w.NHI, w.PR, w.F, s))) return rc;
         const int n_blocks = int(ceil_div(n_local, CHAIN_BLOCK));
         k_chain_blocks<<<dim3(16, (unsigned)n_blocks), 256, 0, s>>>(table, w.F, (int)r_lo, (int)r_hi, w.G);
     }

@@ -12,6 +12,8 @@ import pickle
 import weakref
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -28,6 +30,9 @@ torch.manual_seed(1111)   # src/layers.py:13
 np.random.seed(1111)      # src/layers.py:14 (the device stream is seeded 1111 too, see neg_sampling._state)
 EPS = 1e-13               # src/layers.py:15
 SERIAL_STREAMS = False    # measurement aid (bench.py): keep every kernel of a step on the caller's stream
+# priority of the sampler's side stream in TIP.forward (-1 = above the encoder's stream, 0 = equal).  TIPB_SIDE_PRIORITY
+# overrides it for measurements.
+SIDE_PRIORITY = int(os.environ.get("TIPB_SIDE_PRIORITY", "-1"))
 
 
 def _require_cuda(t, who):
@@ -473,7 +478,7 @@ class TIP(nn.Module):
     def forward(self, check_status=True):
         d = self.data
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # the sampler is the critical chain
+            self._side = torch.cuda.Stream(device=self.device, priority=SIDE_PRIORITY)
         cur = torch.cuda.current_stream(self.device)
         side = cur if SERIAL_STREAMS else self._side
         # ---- fused pair pass (csrc/pair_pass.cu): mirrored edge set + z fits in shared memory (the polypharmacy shape)

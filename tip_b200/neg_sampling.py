@@ -170,7 +170,7 @@ class _Membership(object):
         check(L.tipb_neg_bitmap_build(ptr(_i64c(pos_edge_index)), ptr(self.range_dev), self.n_edges, num_nodes,
                                       self.n_rel, ptr(self.member), ptr(popcount), stream()), "neg_bitmap_build")
         pop = np.ascontiguousarray(popcount.cpu().numpy())             # one-time host copy
-        table = np.zeros((max(self.n_rel, 1), 7), dtype=np.int64)
+        table = np.zeros((max(self.n_rel, 1), 8), dtype=np.int64)
         totals = np.zeros(4, dtype=np.int64)
         check(L.tipb_neg_table_build(rl.ctypes.data_as(C.c_void_p), pop.ctypes.data_as(C.c_void_p), self.n_rel,
                                      num_nodes, Z_SIGMA, table.ctypes.data_as(C.c_void_p),
@@ -359,7 +359,7 @@ class ShardedSampler(object):
 
     def _build_table(self):
         L = lib()
-        table = np.zeros((max(self.n_rel, 1), 7), dtype=np.int64)
+        table = np.zeros((max(self.n_rel, 1), 8), dtype=np.int64)
         totals = np.zeros(4, dtype=np.int64)
         pop = np.ascontiguousarray(self._pop_all)
         check(L.tipb_neg_table_build(self.rl_host.ctypes.data_as(C.c_void_p), pop.ctypes.data_as(C.c_void_p), self.n_rel,
