@@ -379,15 +379,16 @@ def run_b200_arm(args):
     assert int(ns.last_status(dev)) == 0, "negative sampler ran out of pre-generated words"
 
     graph = None
+    main_prio = int(os.environ.get("TIPB_BENCH_MAIN_PRIORITY", "-1"))
     static_loss = None
     if not args.no_graph:
         try:
             model.embeddings = None          # drop the last eager autograd graph before capturing
             opt.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
-            # sharded runs: the main chain (P-P encoder, R-GCN, collectives) is captured on a high-priority stream, the
-            # sampler's side stream has the default priority (tip_b200/parallel.py)
-            cap = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+            # the main chain (P-P encoder, R-GCN, pair pass, backward, collectives) is captured on a high-priority stream, the
+            # sampler's side stream has the default priority (tip_b200/layers.py: SIDE_PRIORITY)
+            cap = torch.cuda.Stream(device=dev, priority=main_prio) if main_prio != 0 else None
             with torch.cuda.graph(graph, stream=cap):
                 static_loss = step().detach()
             for _ in range(2):
@@ -452,6 +453,7 @@ def run_b200_arm(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(workload, args.mod, data, world), "cuda_graph": graph is not None,
+                "stream_priority": {"step": main_prio if graph is not None else 0, "sampler_side_stream": layers.SIDE_PRIORITY},
                 "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                 "all_cuda_kernels_per_step": launches_all, "loss": loss_value}

@@ -464,24 +464,13 @@ int tipb_rgcn_fwd(const void* plan_by_dst, int64_t n_entries, int64_t n_nodes, i
     // kernel then outweighs its main loop, and the tiled kernel with its five CTAs per SM is the faster one)
     static const bool tc_env = [] { const char* e = getenv("TIPB_RGCN_TC"); return !(e && e[0] == '0'); }();
     const bool use_tc = tc_env && n_rel >= RGCN_TC_MIN_REL;
-    /* TIPB_RGCN_TCP=0 selects the one-CTA-per-node tensor-core kernels instead of the persistent ones (measurements) */
-    static const bool tcp_env = [] { const char* e = getenv("TIPB_RGCN_TCP"); return !(e && e[0] == '0'); }();
 #define TC_FWD(FV, NBV)                                                                                            \
     {                                                                                                              \
-        if (tcp_env && rgcn_tc_dbg() == 0) {                                                                       \
-            auto kern = k_rgcn_node_fwd_tcp<FV, NBV>;                                                              \
-            const size_t sm = RpLayout<FV, NBV>::BYTES;                                                            \
-            if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                          \
-            const int64_t grid = n_nodes < sm_count() ? n_nodes : sm_count();                                      \
-            kern<<<(unsigned)grid, RP_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, H, att, g_saved, (int)n_nodes,      \
-                                                        rgcn_tc_error_flag());                                     \
-        } else {                                                                                                   \
-            auto kern = k_rgcn_node_fwd_tc<FV, NBV>;                                                               \
-            const size_t sm = RtLayout<FV, NBV>::BYTES;                                                            \
-            if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                          \
-            kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, H, att, g_saved,                 \
-                                                           rgcn_tc_error_flag(), rgcn_tc_dbg());                   \
-        }                                                                                                          \
+        auto kern = k_rgcn_node_fwd_tc<FV, NBV>;                                                                   \
+        const size_t sm = RtLayout<FV, NBV>::BYTES;                                                                \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, H, att, g_saved, rgcn_tc_error_flag(), \
+                                                       rgcn_tc_dbg());                                             \
         TIPB_CHECK_LAUNCH("rgcn_node_fwd_tc");                                                                     \
         return basis_out_launch(g_saved, basis, v.inv_deg, x, root, bias, (int)n_nodes, f_in, f_out, n_bases,      \
                                 relu_out, out_partial, out, s);                                                    \
@@ -592,26 +581,15 @@ int tipb_rgcn_bwd(const void* plan_by_src, int64_t n_entries, int64_t n_nodes, i
         tiled = true;                                                                                              \
     }
     static const bool tc_env = [] { const char* e = getenv("TIPB_RGCN_TC"); return !(e && (e[0] == '0' || e[0] == '1')); }();
-    /* TIPB_RGCN_TCP=0 (or 1: forward only): the one-CTA-per-node kernel instead of the persistent one (measurements) */
-    static const bool tcp_env = [] { const char* e = getenv("TIPB_RGCN_TCP"); return !(e && (e[0] == '0' || e[0] == '1')); }();
     const bool use_tc = tc_env && n_rel >= RGCN_TC_MIN_REL;
 #define TC_BWD(FOV, NBV)                                                                                           \
     {                                                                                                              \
         if ((rc = basis_y_launch(x, basis, (int)n_nodes, f_in, f_out, n_bases, Ybuf, s))) return rc;               \
-        if (tcp_env && rgcn_tc_dbg() == 0) {                                                                       \
-            auto kern = k_rgcn_node_bwd_tcp<FOV, NBV>;                                                             \
-            const size_t sm = RpBwdLayout<FOV, NBV>::BYTES;                                                        \
-            if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                          \
-            const int64_t grid = n_nodes < sm_count() ? n_nodes : sm_count();                                      \
-            kern<<<(unsigned)grid, RP_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, T, att, Ybuf, datt_seg, Qbuf,       \
-                                                        (int)n_nodes, rgcn_tc_error_flag());                       \
-        } else {                                                                                                   \
-            auto kern = k_rgcn_node_bwd_tc<FOV, NBV>;                                                              \
-            const size_t sm = RtBwdLayout<FOV, NBV>::BYTES;                                                        \
-            if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                          \
-            kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, T, att, Ybuf, datt_seg, Qbuf,    \
-                                                           rgcn_tc_error_flag(), rgcn_tc_dbg());                   \
-        }                                                                                                          \
+        auto kern = k_rgcn_node_bwd_tc<FOV, NBV>;                                                                  \
+        const size_t sm = RtBwdLayout<FOV, NBV>::BYTES;                                                            \
+        if ((rc = ensure_dyn_smem((const void*)kern, sm))) return rc;                                              \
+        kern<<<(unsigned)n_nodes, RT_THREADS, sm, s>>>(v.node_ptr, v.seg_rel, T, att, Ybuf, datt_seg, Qbuf,        \
+                                                       rgcn_tc_error_flag(), rgcn_tc_dbg());                       \
         if ((rc = basis_dx_launch(Qbuf, basis, geff, root, (int)n_nodes, f_in, f_out, n_bases, dx_partial, d_x, s))) return rc; \
         tiled = true;                                                                                              \
     }

@@ -38,7 +38,8 @@ struct RtLayout {
     static constexpr int A_PIECE = (RT_M / 8) * RT_SBO;          // 8 KB
     static constexpr int B_PIECE = (NB / 8) * RT_SBO;            // 4 KB (NB = 32)
     static constexpr int STAGE = 3 * A_PIECE + 3 * B_PIECE;
-    static constexpr size_t BYTES = 2 * size_t(STAGE) + 1024;
+    static constexpr int NS = 2;       // operand stages.  Measured with 3 (216 KB of the SM's 256 KB L1/shared array): 67 -> 79 us
+    static constexpr size_t BYTES = NS * size_t(STAGE) + 1024;
 };
 
 template <int F, int NB>
@@ -54,7 +55,7 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     constexpr int A_ITERS = A_UNITS > 0 ? A_UNITS : 1;
     extern __shared__ __align__(1024) uint8_t rt_smem[];
     uint8_t* stage0 = rt_smem;
-    __shared__ uint64_t bar_free[2], bar_done;
+    __shared__ uint64_t bar_free[LY::NS], bar_done;
     __shared__ uint32_t s_tmem_base;
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -63,8 +64,8 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     const int n_chunks = (se - sb + RT_KC - 1) / RT_KC;
 
     if (tid == 0) {
-        mbar_init(&bar_free[0], 1);
-        mbar_init(&bar_free[1], 1);
+#pragma unroll
+        for (int q = 0; q < LY::NS; ++q) mbar_init(&bar_free[q], 1);
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
@@ -73,10 +74,10 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     // range of every piece (nothing to do for F = 64); the measurement modes zero everything
     if (dbg) {
         if (!(dbg & 128))
-        for (int k = tid; k < 2 * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = tid; k < LY::NS * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
     } else if (F < RT_M) {
         constexpr int Z16 = (RT_M - F) / 8 * RT_SBO / 16;           // 16-byte words per piece
-        for (int k = tid; k < 6 * Z16; k += RT_THREADS) {
+        for (int k = tid; k < 3 * LY::NS * Z16; k += RT_THREADS) {
             const int piece = k / Z16, w = k % Z16;               // piece = stage * 3 + piece index
             uint8_t* base = stage0 + (piece / 3) * LY::STAGE + (piece % 3) * LY::A_PIECE + (F / 8) * RT_SBO;
             reinterpret_cast<uint4*>(base)[w] = make_uint4(0u, 0u, 0u, 0u);
@@ -165,9 +166,10 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     constexpr int piece_a[6] = {0, 0, 1, 1, 0, 2};
     constexpr int piece_b[6] = {0, 1, 0, 1, 2, 0};
     auto chunk_trip = [&](int c, float (&ra)[A_ITERS][8], float (&rb)[8]) {
-        const int st = c & 1;
+        // the MMAs of chunk c - NS must have read this stage (a third stage did not pay: see RtLayout::NS)
+        const int st = c % LY::NS;
         uint8_t* stage = stage0 + st * LY::STAGE;
-        if (c >= 2) ok = mbar_wait(&bar_free[st], ((c >> 1) - 1) & 1u);      // the MMAs of chunk c - 2 have read this stage
+        if (c >= LY::NS) ok = mbar_wait(&bar_free[st], uint32_t(c / LY::NS - 1) & 1u);
         if (!ok) return;
         if (!(dbg & 16)) store_pieces(stage, ra, rb);
         if (c + 2 < n_chunks) load_raw(c + 2, ra, rb);
@@ -219,239 +221,6 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     if (wid == 0 && !(dbg & 64)) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 32);
-    }
-}
-
-// ================================================================================================ persistent forward
-// The per-node kernel above pays its set-up (TMEM allocation, barrier initialisation, a cold pipeline, the drain) once per
-// node and runs 645 CTAs in 2.18 waves of 296: with every load, conversion and MMA removed it still takes 20 us of the
-// 67 us.  Here ONE CTA per SM walks the nodes blockIdx.x, blockIdx.x + gridDim.x, ...; its two halves of 256 threads take
-// the even / odd 64-segment chunks of the current node, each with its own two-stage operand ring, its own MMA-issuing
-// thread and its own TMEM accumulator (G = D_0 + D_1 in the epilogue: a fixed order).  The operand loads run two trips
-// ahead of the conversion and cross node boundaries, so the next node's first chunks are in flight while this node's
-// accumulators drain.  On a barrier time-out nothing is skipped except the waits themselves (every bar.sync stays
-// matched); the error flag reports it.
-constexpr int RP_THREADS = 512;
-constexpr int RP_HALF = 256;
-
-__device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory"); }
-
-template <int F, int NB>
-struct RpLayout {
-    static constexpr int A_PIECE = (RT_M / 8) * RT_SBO;
-    static constexpr int B_PIECE = (NB / 8) * RT_SBO;
-    static constexpr int STAGE = 3 * A_PIECE + 3 * B_PIECE;
-    static constexpr size_t BYTES = 4 * size_t(STAGE) + 1024;      // [half][stage]
-};
-
-// this half's position in its sequence of (node, chunk) trips
-struct RpCursor {
-    int node, ch, sb, se, nch;
-};
-
-template <int F, int NB>
-__global__ void __launch_bounds__(RP_THREADS, 1)
-k_rgcn_node_fwd_tcp(const int* __restrict__ node_ptr, const int* __restrict__ seg_rel, const float* __restrict__ H,
-                    const float* __restrict__ att, float* __restrict__ g_saved, int n_nodes, int* __restrict__ error_flag) {
-    using LY = RpLayout<F, NB>;
-    static_assert(F == 64 || F == 32 || F == 16, "feature width");
-    static_assert(NB == 32 || NB == 16, "number of bases");
-    constexpr int A_UNITS = F * (RT_KC / 8) / RP_HALF;
-    constexpr int A_ITERS = A_UNITS > 0 ? A_UNITS : 1;
-    extern __shared__ __align__(1024) uint8_t rt_smem[];
-    __shared__ uint64_t bar_free[2][2], bar_done[2];
-    __shared__ uint32_t s_tmem_base;
-
-    const int tid = threadIdx.x, half = tid >> 8, ht = tid & (RP_HALF - 1), wid = tid >> 5, lane = tid & 31;
-    uint8_t* stage0 = rt_smem + half * 2 * LY::STAGE;
-    if (tid == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            mbar_init(&bar_free[h][0], 1);
-            mbar_init(&bar_free[h][1], 1);
-            mbar_init(&bar_done[h], 1);
-        }
-        fence_barrier_init();
-    }
-    if (wid == 0) tmem_alloc(&s_tmem_base, 64);
-    if (F < RT_M) {      // rows f >= F of the A tiles are never written and must read as zero
-        constexpr int Z16 = (RT_M - F) / 8 * RT_SBO / 16;
-        for (int k = tid; k < 12 * Z16; k += RP_THREADS) {
-            const int piece = k / Z16, w = k % Z16;               // piece = stage (of 4) * 3 + piece index
-            uint8_t* base = rt_smem + (piece / 3) * LY::STAGE + (piece % 3) * LY::A_PIECE + (F / 8) * RT_SBO;
-            reinterpret_cast<uint4*>(base)[w] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = s_tmem_base + uint32_t(half) * 32u;
-
-    const int af = ht % F, ao = ht / F;
-    const int bb = ht % NB, bo = ht / NB;
-    const bool a_live = (F * (RT_KC / 8) >= RP_HALF) || ao < RT_KC / 8;
-    const bool b_live = bo < RT_KC / 8;
-
-    auto enter = [&](RpCursor& c) {            // position c on the first chunk of node c.node for this half (or past the end)
-        while (c.node < n_nodes) {
-            c.sb = node_ptr[c.node];
-            c.se = node_ptr[c.node + 1];
-            c.nch = (c.se - c.sb + RT_KC - 1) / RT_KC;
-            c.ch = half;
-            if (c.ch < c.nch) return;
-            c.node += gridDim.x;
-        }
-    };
-    auto advance = [&](RpCursor& c) {
-        c.ch += 2;
-        if (c.ch >= c.nch) {
-            c.node += gridDim.x;
-            enter(c);
-        }
-    };
-    auto load_raw = [&](const RpCursor& c, float (&ra)[A_ITERS][8], float (&rb)[8]) {
-        if (c.node >= n_nodes) return;
-        const int s0 = c.sb + c.ch * RT_KC, se = c.se;
-        const float* pa = H + int64_t(s0 + ao * 8) * F + af;
-        const int* pr = seg_rel + s0 + bo * 8;
-        if (s0 + RT_KC <= se) {
-            if (a_live) {
-#pragma unroll
-                for (int u = 0; u < A_ITERS; ++u)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) ra[u][j] = pa[(u * (RP_HALF / F) * 8 + j) * F];
-            }
-            if (b_live) {
-                int rel[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rel[j] = pr[j];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rb[j] = att[rel[j] * NB + bb];
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < A_ITERS; ++u) {
-                const int oct = ao + u * (RP_HALF / F);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int sg = s0 + oct * 8 + j;
-                    ra[u][j] = (a_live && sg < se) ? pa[(u * (RP_HALF / F) * 8 + j) * F] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int sg = s0 + bo * 8 + j;
-                rb[j] = (b_live && sg < se) ? att[pr[j] * NB + bb] : 0.f;
-            }
-        }
-    };
-    auto store_pieces = [&](uint8_t* st, const float (&ra)[A_ITERS][8], const float (&rb)[8]) {
-#pragma unroll
-        for (int u = 0; u < A_ITERS; ++u) {
-            if (!a_live) continue;
-            const int oct = ao + u * (RP_HALF / F);
-            const Pieces8 p = split8(ra[u]);
-            const uint32_t off = rt_chunk_offset(af, oct);
-            *reinterpret_cast<uint4*>(st + off) = p.hi;
-            *reinterpret_cast<uint4*>(st + LY::A_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(st + 2 * LY::A_PIECE + off) = p.lo;
-        }
-        if (b_live) {
-            const Pieces8 p = split8(rb);
-            uint8_t* sbm = st + 3 * LY::A_PIECE;
-            const uint32_t off = rt_chunk_offset(bb, bo);
-            *reinterpret_cast<uint4*>(sbm + off) = p.hi;
-            *reinterpret_cast<uint4*>(sbm + LY::B_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(sbm + 2 * LY::B_PIECE + off) = p.lo;
-        }
-    };
-
-    bool ok = true;
-    float ra0[A_ITERS][8], rb0[8], ra1[A_ITERS][8], rb1[8];
-    RpCursor lc;                                 // load cursor: two trips ahead of the trip being converted
-    lc.node = blockIdx.x;
-    lc.ch = 0; lc.sb = 0; lc.se = 0; lc.nch = 0;
-    enter(lc);
-    load_raw(lc, ra0, rb0);
-    advance(lc);
-    load_raw(lc, ra1, rb1);
-    advance(lc);
-
-    constexpr uint32_t idesc = umma_idesc_bf16(RT_M, NB);
-    constexpr int piece_a[6] = {0, 0, 1, 1, 0, 2};
-    constexpr int piece_b[6] = {0, 1, 0, 1, 2, 0};
-    uint32_t t = 0;                              // trips of this half so far (uniform over the half)
-    // one trip: registers -> stage t & 1, reload the registers for trip t + 2, MMAs of the chunk
-    auto trip = [&](float (&ra)[A_ITERS][8], float (&rb)[8], bool first, bool last) {
-        const int st = int(t & 1u);
-        uint8_t* stage = stage0 + st * LY::STAGE;
-        if (t >= 2 && ok) ok = mbar_wait(&bar_free[half][st], ((t >> 1) - 1) & 1u);
-        store_pieces(stage, ra, rb);
-        load_raw(lc, ra, rb);
-        advance(lc);
-        fence_proxy_async();
-        half_sync(half);
-        if (ht == 0) {
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(stage), b_base = a_base + 3 * LY::A_PIECE;
-#pragma unroll
-            for (int kk = 0; kk < RT_KC / 16; ++kk) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p) {
-                    const uint64_t da = umma_desc(a_base + piece_a[p] * LY::A_PIECE + kk * 256, 128, RT_SBO);
-                    const uint64_t db = umma_desc(b_base + piece_b[p] * LY::B_PIECE + kk * 256, 128, RT_SBO);
-                    umma_bf16(tmem_d, da, db, idesc, (!first || kk > 0 || p > 0) ? 1u : 0u);
-                }
-            }
-            umma_commit(&bar_free[half][st]);
-            if (last) umma_commit(&bar_done[half]);
-        }
-        ++t;
-    };
-
-    uint32_t done_phase[2] = {0u, 0u};
-    for (int node = blockIdx.x; node < n_nodes; node += gridDim.x) {
-        const int sb = node_ptr[node], se = node_ptr[node + 1];
-        const int nch = (se - sb + RT_KC - 1) / RT_KC;
-        const int n_mine = nch > half ? (nch - half + 1) >> 1 : 0;
-        for (int q = 0; q < n_mine; ++q) {
-            if ((t & 1u) == 0u) trip(ra0, rb0, q == 0, q + 1 == n_mine);
-            else trip(ra1, rb1, q == 0, q + 1 == n_mine);
-        }
-        __syncthreads();                         // both halves have issued this node's MMAs
-        // ---- G: TMEM -> global.  Row f lives in lane (f % 16) + 32 (f / 16): warp w < F / 16 holds rows 16 w .. + 15
-        const bool has0 = nch > 0, has1 = nch > 1;
-        if (wid < F / 16) {
-            if (has0 && ok) ok = mbar_wait(&bar_done[0], done_phase[0]);
-            if (has1 && ok) ok = mbar_wait(&bar_done[1], done_phase[1]);
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < NB; c0 += 16) {          // 16 columns at a time: 32 live registers, not 64
-                uint32_t v0[16], v1[16];
-                if (has0) tmem_ld16(s_tmem_base + (uint32_t(wid * 32) << 16) + uint32_t(c0), v0);
-                if (has1) tmem_ld16(s_tmem_base + (uint32_t(wid * 32) << 16) + 32u + uint32_t(c0), v1);
-                tmem_ld_wait();
-                if (lane < 16) {
-                    const int f = wid * 16 + lane;
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const float g = (has0 ? __uint_as_float(v0[b]) : 0.f) + (has1 ? __uint_as_float(v1[b]) : 0.f);
-                        g_saved[(int64_t(node) * NB + c0 + b) * F + f] = g;
-                    }
-                }
-            }
-            tc_fence_before();
-        }
-        if (has0) done_phase[0] ^= 1u;
-        if (has1) done_phase[1] ^= 1u;
-        __syncthreads();                         // the accumulators are drained before the next node overwrites them
-    }
-    if (!ok) atomicExch(error_flag, 3);
-    tc_fence_before();
-    __syncthreads();
-    if (wid == 0) {
-        tc_fence_after();
-        tmem_dealloc(s_tmem_base, 64);
     }
 }
 
@@ -693,287 +462,6 @@ k_rgcn_node_bwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
     if (wid == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 128);
-    }
-}
-
-// ================================================================================================ persistent backward
-// The same persistent form for the backward node pass (see k_rgcn_node_bwd_tc for the math): one CTA per SM, two halves
-// on the even / odd chunks of the current node.  Per half: a two-stage operand ring (A1 = T^T, B1 = att rows, A2 = T),
-// the accumulator D1 (Q partial; Q = D1_0 + D1_1 in the node epilogue) and two alternating D2 accumulators (d_att of a
-// chunk's segments, drained while the next chunk's MMAs run).  B2 = the pieces of Y_j is shared by the halves and
-// rebuilt per node from registers loaded one node ahead.
-template <int FO, int NB>
-struct RpBwdLayout {
-    static constexpr int A1_PIECE = (RT_M / 8) * RT_SBO;
-    static constexpr int B1_PIECE = (NB / 8) * RT_SBO;
-    static constexpr int SBO2 = (FO / 8) * 128;
-    static constexpr int A2_PIECE = (RT_KC / 8) * SBO2;
-    static constexpr int B2_PIECE = (NB / 8) * SBO2;
-    static constexpr int STAGE = 3 * (A1_PIECE + B1_PIECE + A2_PIECE);
-    static constexpr size_t BYTES = 4 * size_t(STAGE) + 3 * size_t(B2_PIECE) + 1024;
-};
-
-template <int FO, int NB>
-__global__ void __launch_bounds__(RP_THREADS, 1)
-k_rgcn_node_bwd_tcp(const int* __restrict__ node_ptr, const int* __restrict__ seg_rel, const float* __restrict__ T,
-                    const float* __restrict__ att, const float* __restrict__ Y, float* __restrict__ datt_seg,
-                    float* __restrict__ Q, int n_nodes, int* __restrict__ error_flag) {
-    using LY = RpBwdLayout<FO, NB>;
-    static_assert(FO == 32 || FO == 16, "payload width");
-    static_assert(NB == 32 || NB == 16, "number of bases");
-    constexpr uint32_t HALF_COLS = 96;          // D1 | D2[0] | D2[1], 32 columns each
-    extern __shared__ __align__(1024) uint8_t rt_smem[];
-    uint8_t* sB2 = rt_smem + 4 * LY::STAGE;
-    __shared__ uint64_t bar_free[2][2];
-    __shared__ uint32_t s_tmem_base;
-
-    const int tid = threadIdx.x, half = tid >> 8, ht = tid & (RP_HALF - 1), wid = tid >> 5, hw = wid & 7, lane = tid & 31;
-    uint8_t* stage0 = rt_smem + half * 2 * LY::STAGE;
-    if (tid == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            mbar_init(&bar_free[h][0], 1);
-            mbar_init(&bar_free[h][1], 1);
-        }
-        fence_barrier_init();
-    }
-    if (wid == 0) tmem_alloc(&s_tmem_base, 256);
-    {   // rows o >= FO of the A1 tiles are never written and must read as zero
-        constexpr int Z16 = (RT_M - FO) / 8 * RT_SBO / 16;
-        for (int k = tid; k < 12 * Z16; k += RP_THREADS) {
-            const int piece = k / Z16, w = k % Z16;
-            uint8_t* base = rt_smem + (piece / 3) * LY::STAGE + (piece % 3) * LY::A1_PIECE + (FO / 8) * RT_SBO;
-            reinterpret_cast<uint4*>(base)[w] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_h = s_tmem_base + uint32_t(half) * HALF_COLS;
-
-    const int ao1 = ht % FO, a1o = ht / FO;
-    const int bb = ht % NB, bo = ht / NB;
-    const int a2s = ht / (FO / 8), a2o = ht % (FO / 8);
-    const bool a1_live = a1o < RT_KC / 8, b_live = bo < RT_KC / 8, a2_live = a2s < RT_KC;
-    const bool y_live = tid < NB * (FO / 8);
-    const int yb = tid / (FO / 8), yoc = tid % (FO / 8);
-
-    auto enter = [&](RpCursor& c) {
-        while (c.node < n_nodes) {
-            c.sb = node_ptr[c.node];
-            c.se = node_ptr[c.node + 1];
-            c.nch = (c.se - c.sb + RT_KC - 1) / RT_KC;
-            c.ch = half;
-            if (c.ch < c.nch) return;
-            c.node += gridDim.x;
-        }
-    };
-    auto advance = [&](RpCursor& c) {
-        c.ch += 2;
-        if (c.ch >= c.nch) {
-            c.node += gridDim.x;
-            enter(c);
-        }
-    };
-    auto load_raw = [&](const RpCursor& c, float (&ra)[8], float (&rb)[8], float (&r2)[8]) {
-        if (c.node >= n_nodes) return;
-        const int s0 = c.sb + c.ch * RT_KC, se = c.se;
-        const float* pa = T + int64_t(s0 + a1o * 8) * FO + ao1;
-        const int* pr = seg_rel + s0 + bo * 8;
-        const float4* t4 = reinterpret_cast<const float4*>(T + int64_t(s0 + a2s) * FO + a2o * 8);
-        if (s0 + RT_KC <= se) {
-            if (a1_live) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) ra[q] = pa[q * FO];
-            }
-            if (b_live) {
-                int rel[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) rel[q] = pr[q];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) rb[q] = att[rel[q] * NB + bb];
-            }
-            if (a2_live) {
-                const float4 u0 = t4[0], u1 = t4[1];
-                r2[0] = u0.x; r2[1] = u0.y; r2[2] = u0.z; r2[3] = u0.w; r2[4] = u1.x; r2[5] = u1.y; r2[6] = u1.z; r2[7] = u1.w;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int s1 = s0 + a1o * 8 + q, s2 = s0 + bo * 8 + q;
-                ra[q] = (a1_live && s1 < se) ? pa[q * FO] : 0.f;
-                rb[q] = (b_live && s2 < se) ? att[pr[q] * NB + bb] : 0.f;
-            }
-            if (a2_live && s0 + a2s < se) {
-                const float4 u0 = t4[0], u1 = t4[1];
-                r2[0] = u0.x; r2[1] = u0.y; r2[2] = u0.z; r2[3] = u0.w; r2[4] = u1.x; r2[5] = u1.y; r2[6] = u1.z; r2[7] = u1.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) r2[q] = 0.f;
-            }
-        }
-    };
-    auto store_pieces = [&](uint8_t* st, const float (&ra)[8], const float (&rb)[8], const float (&r2)[8]) {
-        uint8_t* sA1 = st;
-        uint8_t* sB1 = st + 3 * LY::A1_PIECE;
-        uint8_t* sA2 = sB1 + 3 * LY::B1_PIECE;
-        if (a1_live) {
-            const Pieces8 p = split8(ra);
-            const uint32_t off = rt_chunk_offset(ao1, a1o);
-            *reinterpret_cast<uint4*>(sA1 + off) = p.hi;
-            *reinterpret_cast<uint4*>(sA1 + LY::A1_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(sA1 + 2 * LY::A1_PIECE + off) = p.lo;
-        }
-        if (b_live) {
-            const Pieces8 p = split8(rb);
-            const uint32_t off = rt_chunk_offset(bb, bo);
-            *reinterpret_cast<uint4*>(sB1 + off) = p.hi;
-            *reinterpret_cast<uint4*>(sB1 + LY::B1_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(sB1 + 2 * LY::B1_PIECE + off) = p.lo;
-        }
-        if (a2_live) {
-            const Pieces8 p = split8(r2);
-            const uint32_t off = uint32_t((a2s >> 3) * LY::SBO2 + a2o * 128 + (a2s & 7) * 16);
-            *reinterpret_cast<uint4*>(sA2 + off) = p.hi;
-            *reinterpret_cast<uint4*>(sA2 + LY::A2_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(sA2 + 2 * LY::A2_PIECE + off) = p.lo;
-        }
-    };
-    auto load_y = [&](int node, float (&ry)[8]) {
-        if (!y_live || node >= n_nodes) return;
-        const float4* y4 = reinterpret_cast<const float4*>(Y + (int64_t(node) * NB + yb) * FO + yoc * 8);
-        const float4 u0 = y4[0], u1 = y4[1];
-        ry[0] = u0.x; ry[1] = u0.y; ry[2] = u0.z; ry[3] = u0.w; ry[4] = u1.x; ry[5] = u1.y; ry[6] = u1.z; ry[7] = u1.w;
-    };
-
-    bool ok = true;
-    // D2 of trip tt (a chunk of this half starting at segment s_base): rows s = 16 hw + lane (lane < 16) of warp hw < 4
-    auto drain_d2 = [&](uint32_t tt, int s_base, int se) {
-        if (hw >= 4) return;
-        if (ok) ok = mbar_wait(&bar_free[half][tt & 1u], (tt >> 1) & 1u);
-        tc_fence_after();
-        const int sg = s_base + hw * 16 + lane;
-#pragma unroll
-        for (int c0 = 0; c0 < NB; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_h + (uint32_t(hw * 32) << 16) + 32u + (tt & 1u) * 32u + uint32_t(c0), v);
-            tmem_ld_wait();
-            if (lane < 16 && sg < se) {
-                float4* dst = reinterpret_cast<float4*>(datt_seg + int64_t(sg) * NB + c0);
-#pragma unroll
-                for (int b4 = 0; b4 < 4; ++b4)
-                    dst[b4] = make_float4(__uint_as_float(v[4 * b4]), __uint_as_float(v[4 * b4 + 1]),
-                                          __uint_as_float(v[4 * b4 + 2]), __uint_as_float(v[4 * b4 + 3]));
-            }
-        }
-        tc_fence_before();
-    };
-
-    float ra0[8], rb0[8], r20[8], ra1[8], rb1[8], r21[8], ry[8];
-    RpCursor lc;
-    lc.node = blockIdx.x;
-    lc.ch = 0; lc.sb = 0; lc.se = 0; lc.nch = 0;
-    enter(lc);
-    load_raw(lc, ra0, rb0, r20);
-    advance(lc);
-    load_raw(lc, ra1, rb1, r21);
-    advance(lc);
-    load_y(blockIdx.x, ry);
-
-    constexpr uint32_t idesc = umma_idesc_bf16(RT_M, NB);
-    constexpr int piece_a[6] = {0, 0, 1, 1, 0, 2};
-    constexpr int piece_b[6] = {0, 1, 0, 1, 2, 0};
-    uint32_t t = 0;
-    auto trip = [&](float (&ra)[8], float (&rb)[8], float (&r2)[8], bool first, int prev_base, int se) {
-        const int st = int(t & 1u);
-        uint8_t* stage = stage0 + st * LY::STAGE;
-        if (t >= 2 && ok) ok = mbar_wait(&bar_free[half][st], ((t >> 1) - 1) & 1u);
-        store_pieces(stage, ra, rb, r2);
-        load_raw(lc, ra, rb, r2);
-        advance(lc);
-        fence_proxy_async();
-        half_sync(half);                          // (also: D2 of trip t - 2 was drained in the previous trip)
-        if (ht == 0) {
-            tc_fence_after();
-            const uint32_t a1 = smem_u32(stage), b1 = a1 + 3 * LY::A1_PIECE, a2 = b1 + 3 * LY::B1_PIECE, b2 = smem_u32(sB2);
-#pragma unroll
-            for (int kk = 0; kk < RT_KC / 16; ++kk) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p) {
-                    const uint64_t da = umma_desc(a1 + piece_a[p] * LY::A1_PIECE + kk * 256, 128, RT_SBO);
-                    const uint64_t db = umma_desc(b1 + piece_b[p] * LY::B1_PIECE + kk * 256, 128, RT_SBO);
-                    umma_bf16(tmem_h, da, db, idesc, (!first || kk > 0 || p > 0) ? 1u : 0u);
-                }
-            }
-#pragma unroll
-            for (int kk = 0; kk < FO / 16; ++kk) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p) {
-                    const uint64_t da = umma_desc(a2 + piece_a[p] * LY::A2_PIECE + kk * 256, 128, LY::SBO2);
-                    const uint64_t db = umma_desc(b2 + piece_b[p] * LY::B2_PIECE + kk * 256, 128, LY::SBO2);
-                    umma_bf16(tmem_h + 32u + uint32_t(st) * 32u, da, db, idesc, (kk > 0 || p > 0) ? 1u : 0u);
-                }
-            }
-            umma_commit(&bar_free[half][st]);
-        }
-        if (!first) drain_d2(t - 1, prev_base, se);        // while the tensor core works on this chunk
-        ++t;
-    };
-
-    for (int node = blockIdx.x; node < n_nodes; node += gridDim.x) {
-        const int sb = node_ptr[node], se = node_ptr[node + 1];
-        const int nch = (se - sb + RT_KC - 1) / RT_KC;
-        const int n_mine = nch > half ? (nch - half + 1) >> 1 : 0;
-        // B2 pieces (rows b, K = o) of this node from the registers loaded one node ago
-        if (y_live && nch > 0) {
-            const Pieces8 p = split8(ry);
-            const uint32_t off = uint32_t((yb >> 3) * LY::SBO2 + yoc * 128 + (yb & 7) * 16);
-            *reinterpret_cast<uint4*>(sB2 + off) = p.hi;
-            *reinterpret_cast<uint4*>(sB2 + LY::B2_PIECE + off) = p.mid;
-            *reinterpret_cast<uint4*>(sB2 + 2 * LY::B2_PIECE + off) = p.lo;
-        }
-        load_y(node + gridDim.x, ry);
-        fence_proxy_async();
-        __syncthreads();                          // B2 is in place for both halves
-        for (int q = 0; q < n_mine; ++q) {
-            const int prev_base = sb + (half + 2 * (q - 1)) * RT_KC;
-            if ((t & 1u) == 0u) trip(ra0, rb0, r20, q == 0, prev_base, se);
-            else trip(ra1, rb1, r21, q == 0, prev_base, se);
-        }
-        // the last chunk's D2; its completion = every MMA of this half for the node is done
-        if (n_mine > 0) drain_d2(t - 1, sb + (half + 2 * (n_mine - 1)) * RT_KC, se);
-        if (n_mine > 0 && hw >= 4 && ok) ok = mbar_wait(&bar_free[half][(t - 1) & 1u], ((t - 1) >> 1) & 1u);
-        tc_fence_before();
-        __syncthreads();                          // both halves: all MMAs of the node completed, D2 drained
-        tc_fence_after();
-        // ---- Q = D1_0 + D1_1: TMEM -> global.  Row o lives in lane (o % 16) + 32 (o / 16)
-        const bool has0 = nch > 0, has1 = nch > 1;
-        if (wid < FO / 16) {
-#pragma unroll
-            for (int c0 = 0; c0 < NB; c0 += 16) {
-                uint32_t v0[16], v1[16];
-                if (has0) tmem_ld16(s_tmem_base + (uint32_t(wid * 32) << 16) + uint32_t(c0), v0);
-                if (has1) tmem_ld16(s_tmem_base + (uint32_t(wid * 32) << 16) + HALF_COLS + uint32_t(c0), v1);
-                tmem_ld_wait();
-                if (lane < 16) {
-                    const int o = wid * 16 + lane;
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const float qv = (has0 ? __uint_as_float(v0[b]) : 0.f) + (has1 ? __uint_as_float(v1[b]) : 0.f);
-                        Q[(int64_t(node) * NB + c0 + b) * FO + o] = qv;
-                    }
-                }
-            }
-            tc_fence_before();
-        }
-        __syncthreads();                          // accumulators and B2 are free for the next node
-    }
-    if (!ok) atomicExch(error_flag, 4);
-    tc_fence_before();
-    __syncthreads();
-    if (wid == 0) {
-        tc_fence_after();
-        tmem_dealloc(s_tmem_base, 256);
     }
 }
 

@@ -152,6 +152,11 @@ class _ShardedRGCN(torch.autograd.Function):
         return d_x, d_basis, d_att, d_root, None, None, None, None, None
 
 
+def _layers_side_priority():
+    from . import layers as _l
+    return _l.SIDE_PRIORITY
+
+
 class ShardedTIP(TIP):
     """TIP whose D-D relations (R-GCN messages, decoder pairs, positive-pair bitmaps, negatives) are sharded over
     `world` ranks.  Every rank constructs the same parameters (same torch seed) and is given the same data; `rank`
@@ -286,9 +291,8 @@ class ShardedTIP(TIP):
     def forward(self, check_status=True):
         d = self.data
         if self._side is None:
-            # one rank's share of the encoder is short: with more than one rank the main chain (replicated P-P encoder,
-            # collectives) is the critical one and the sampler must not take its SM slots
-            self._side = torch.cuda.Stream(device=self.device, priority=-1 if self.world == 1 else 0)
+            # the main chain (P-P encoder, R-GCN, collectives) is the critical one: the sampler must not take its SM slots
+            self._side = torch.cuda.Stream(device=self.device, priority=_layers_side_priority())
         cur = torch.cuda.current_stream(self.device)
         from . import layers as _layers
         side = cur if _layers.SERIAL_STREAMS else self._side

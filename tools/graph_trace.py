@@ -33,7 +33,8 @@ torch.cuda.synchronize()
 model.embeddings = None
 opt.zero_grad(set_to_none=True)
 g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
+_mp = int(os.environ.get("TIPB_BENCH_MAIN_PRIORITY", "0"))     # as bench.py: priority of the capture stream
+with torch.cuda.graph(g, stream=torch.cuda.Stream(priority=_mp) if _mp != 0 else None):
     step()
 for _ in range(3):
     g.replay()
