@@ -145,10 +145,15 @@ k_accept_count(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_
     }
 }
 
+// accepted values of a chunk are compacted in shared memory and written out as whole lines (a thread's own run of up to
+// eight values starts at an arbitrary offset: written directly, every store instruction of the warp touched ~25 sectors).
+// The word position of an accepted value is needed for ONE value per call only (the last one consumed): k_finalize
+// recomputes it from the chunk offsets instead of a second 35 MB array.
 __global__ void __launch_bounds__(ACC_THREADS)
 k_compact(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, int64_t n_words, uint32_t mask,
-          uint32_t max_val, const int* __restrict__ chunk_off, int* __restrict__ A, int* __restrict__ Apos) {
+          uint32_t max_val, const int* __restrict__ chunk_off, int* __restrict__ A) {
     __shared__ int sw[ACC_THREADS / 32];
+    __shared__ int sA[ACC_CHUNK];
     uint32_t w[ACC_ITEMS];
     const int64_t base = int64_t(blockIdx.x) * ACC_CHUNK + int64_t(threadIdx.x) * ACC_ITEMS;
     const unsigned bits = accept_bits(U, base, n_words, int64_t(*pos_ptr), mask, max_val, w);
@@ -161,16 +166,19 @@ k_compact(const uint32_t* __restrict__ U, const uint32_t* __restrict__ pos_ptr, 
     }
     if (lane_id() == 31) sw[warp_id()] = incl;
     __syncthreads();
-    int a = chunk_off[blockIdx.x] + incl - c;
-    for (int k = 0; k < warp_id(); ++k) a += sw[k];
+    int a = incl - c, total = 0;
+#pragma unroll
+    for (int k = 0; k < ACC_THREADS / 32; ++k) {
+        if (k < warp_id()) a += sw[k];
+        total += sw[k];
+    }
 #pragma unroll
     for (int i = 0; i < ACC_ITEMS; ++i) {
-        if ((bits >> i) & 1u) {
-            A[a] = int(w[i]);
-            Apos[a] = int(base + i);
-            ++a;
-        }
+        if ((bits >> i) & 1u) sA[a++] = int(w[i]);
     }
+    __syncthreads();
+    int* dst = A + chunk_off[blockIdx.x];
+    for (int i = threadIdx.x; i < total; i += ACC_THREADS) dst[i] = sA[i];
 }
 
 __device__ __forceinline__ bool is_member(const uint32_t* __restrict__ bits, int key) {
@@ -797,15 +805,59 @@ k_materialize_exact(const int* __restrict__ A, const uint32_t* __restrict__ memb
 }
 
 // ================================================================================================
-__global__ void __launch_bounds__(256)
-k_finalize(const uint32_t* __restrict__ U, const int* __restrict__ Apos, const int* __restrict__ chain_out,
+// the call consumed the accepted values [0, consumed): the MT19937 state moves to the word after the last of them.  Its
+// position in the raw stream: the chunk whose offset range holds it (binary search over the scanned chunk counts), then
+// the chunk's acceptance flags once more (one CTA = one chunk of k_compact).
+__global__ void __launch_bounds__(ACC_THREADS)
+k_finalize(const uint32_t* __restrict__ U, int64_t n_words, uint32_t mask, uint32_t max_val,
+           const int* __restrict__ chunk_off, int n_chunks, const int* __restrict__ chain_out,
            const int* __restrict__ call_status, int* __restrict__ sticky_status, uint32_t* __restrict__ state) {
     __shared__ int64_t s_flat;
+    __shared__ int s_chunk, s_target;
+    __shared__ int sw[ACC_THREADS / 32];
     if (threadIdx.x == 0) {
         const int failed = *call_status;
         if (failed) atomicOr(sticky_status, failed);   // sticky: only the host clears it
         const int consumed = chain_out[0];
-        s_flat = (!failed && consumed > 0) ? int64_t(Apos[consumed - 1]) + 1 : -1;   // a failed call consumes nothing
+        s_flat = -1;                                   // a failed call consumes nothing
+        s_chunk = -1;
+        if (!failed && consumed > 0 && consumed <= chunk_off[n_chunks]) {
+            int lo = 0, hi = n_chunks - 1;             // last chunk with chunk_off[c] <= consumed - 1
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (chunk_off[mid] <= consumed - 1) lo = mid; else hi = mid - 1;
+            }
+            s_chunk = lo;
+            s_target = consumed - 1 - chunk_off[lo];   // rank of the value inside its chunk
+        }
+    }
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk < 0) return;
+    uint32_t w[ACC_ITEMS];
+    const int64_t base = int64_t(chunk) * ACC_CHUNK + int64_t(threadIdx.x) * ACC_ITEMS;
+    const unsigned bits = accept_bits(U, base, n_words, int64_t(state[MT_N]), mask, max_val, w);
+    const int c = __popc(bits);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, o);
+        if (lane_id() >= o) incl += y;
+    }
+    if (lane_id() == 31) sw[warp_id()] = incl;
+    __syncthreads();
+    int before = incl - c;
+    for (int k = 0; k < warp_id(); ++k) before += sw[k];
+    const int t = s_target - before;                   // rank inside this thread's run
+    if (t >= 0 && t < c) {
+        int seen = 0;
+#pragma unroll
+        for (int i = 0; i < ACC_ITEMS; ++i) {
+            if ((bits >> i) & 1u) {
+                if (seen == t) s_flat = base + i + 1;
+                ++seen;
+            }
+        }
     }
     __syncthreads();
     const int64_t flat = s_flat;  // index (in U) of the next unread word
@@ -852,7 +904,7 @@ k_bitmap_popcount(const uint32_t* __restrict__ member, int64_t words_per_rel, in
 static int64_t bitmap_words(int64_t n_nodes) { return (n_nodes * n_nodes + 31) / 32; }
 
 struct NegWs {
-    int *flags, *A, *Apos, *NHI, *PR, *F, *G, *off, *chain_out, *call_status;
+    int *flags, *A, *NHI, *PR, *F, *G, *off, *chain_out, *call_status;
     int *perm, *rounds, *round_ptr, *n_rounds;
     int round_cap;
     void* scan_ws;
@@ -863,7 +915,6 @@ static size_t neg_ws_layout(int64_t n_edges, int64_t n_rel, int64_t n_words, int
     NegWs t;
     t.flags = c.take<int>(n_words + 2);
     t.A = c.take<int>(n_words + 2);
-    t.Apos = c.take<int>(n_words + 2);
     t.NHI = c.take<int>(sum_l + 1);
     t.PR = c.take<int>(sum_l + 1);
     t.F = c.take<int>(sum_w + 1024);  // slack: the chain walk stages 2 KB windows with 16-byte copies
@@ -1020,7 +1071,7 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
     k_accept_count<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
     if ((rc = exclusive_scan_i32(w.flags, w.flags, n_chunks, w.scan_ws, s))) return rc;
     k_compact<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
-                                                         w.A, w.Apos);
+                                                         w.A);
     const int* n_acc = w.flags + n_chunks;
     if (exact_mode) {
         k_chain_exact<<<1, 1024, 0, s>>>(w.A, n_acc, member, wpr, range_list, (int)n_rel, w.round_cap, w.rounds,
@@ -1047,7 +1098,8 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
         k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off, w.NHI, (int)n_rel,
                                                           (int)n_nodes, n_edges, 0, 0, neg_edge_index, neg_packed);
     }
-    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, call_status, status, mt_state);
+    k_finalize<<<1, ACC_THREADS, 0, s>>>(stream_words, n_words, mask, max_val, w.flags, (int)n_chunks, w.chain_out, call_status,
+                                         status, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample");
     return TIPB_OK;
 }
@@ -1090,7 +1142,7 @@ int tipb_neg_sample_shard_begin(const uint32_t* mt_state, const uint32_t* stream
     k_accept_count<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags);
     if ((rc = exclusive_scan_i32(w.flags, w.flags, n_chunks, w.scan_ws, s))) return rc;
     k_compact<<<(unsigned)n_chunks, ACC_THREADS, 0, s>>>(stream_words, mt_state + MT_N, n_words, mask, max_val, w.flags,
-                                                         w.A, w.Apos);
+                                                         w.A);
     const int* n_acc = w.flags + n_chunks;
     const int64_t n_local = r_hi - r_lo;
     if (n_local > 0) {
@@ -1123,6 +1175,9 @@ int tipb_neg_sample_shard_end(uint32_t* mt_state, const uint32_t* stream_words, 
     NegWs w;
     neg_ws_layout(n_edges, n_rel, n_words, sum_l, sum_w, ws, &w);
     const int64_t wpr = bitmap_words(n_nodes);
+    const uint32_t max_val = uint32_t(n_nodes * n_nodes - 1);
+    uint32_t mask = 1;
+    while (mask < max_val) mask = (mask << 1) | 1u;
     // the relation range is read on the device from first_rel; the host passes the matching edge range
     k_chain_resolve<<<1, CHAIN_MAX_BLOCKS, 0, s>>>(table, w.F, w.G, all_tables, first_rel, world, rank, (int)w_max, w.off,
                                                    w.chain_out, w.call_status);
@@ -1135,7 +1190,8 @@ int tipb_neg_sample_shard_end(uint32_t* mt_state, const uint32_t* stream_words, 
         k_materialize_fixup<<<(unsigned)(r_hi - r_lo), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off, w.NHI,
                                                                   (int)r_hi, (int)n_nodes, e_local, (int)r_lo, e_lo,
                                                                   neg_local, packed_local);
-    k_finalize<<<1, 256, 0, s>>>(stream_words, w.Apos, w.chain_out, w.call_status, status, mt_state);
+    k_finalize<<<1, ACC_THREADS, 0, s>>>(stream_words, n_words, mask, max_val, w.flags, (int)ceil_div(n_words, ACC_CHUNK), w.chain_out,
+                                         w.call_status, status, mt_state);
     TIPB_CHECK_LAUNCH("neg_sample_shard_end");
     return TIPB_OK;
 }

@@ -146,6 +146,9 @@ k_decoder_sweep_tc(const float* __restrict__ z, const float* __restrict__ w, int
                         continue;
                     }
                     if (have_lanes) {
+                        // (measured: replacing rcp by three Newton steps on the FMA pipe -- half the SFU work, 2.5x the
+                        // instructions -- made the sweep slower, 460 -> 513 us: the sixteen epilogue warps are bound by
+                        // instruction issue and latency, not by the SFU)
                         if (apply_sigmoid & 1) {                   // 1 / (1 + 2^(-v log2 e)): two SFU operations per score
 #pragma unroll
                             for (int q = 0; q < 32; ++q) {

@@ -35,6 +35,7 @@ SERIAL_STREAMS = False    # measurement aid (bench.py): keep every kernel of a s
 # (bench.py does: torch.cuda.Stream(priority=-1)) lets the encoder's kernels take SM slots first and the sampler fill the
 # gaps: 1.98 -> 1.86 ms per step (profiles/r03m_*).  TIPB_SIDE_PRIORITY overrides it for measurements.
 SIDE_PRIORITY = int(os.environ.get("TIPB_SIDE_PRIORITY", "0"))
+ENCODER_FIRST = os.environ.get("TIPB_ENCODER_FIRST", "1") != "0"
 
 
 def _require_cuda(t, who):
@@ -490,11 +491,19 @@ class TIP(nn.Module):
         if plan is not None:
             if self._neg_packed is None or self._neg_packed.numel() != d.dd_train_idx.shape[1]:
                 self._neg_packed = torch.empty(d.dd_train_idx.shape[1], dtype=torch.int32, device=self.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):    # the negatives do not depend on the encoder: sample them meanwhile
+            # the negatives do not depend on the encoder: both chains fork here.  The encoder (the longer chain) is
+            # enqueued FIRST: a captured graph starts its root branches in capture order, and the sampler's first
+            # kernels are wide enough to keep the encoder's first kernel waiting for SM slots otherwise
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            if ENCODER_FIRST:
+                self.embeddings = self._encode()
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
                 typed_negative_sampling(d.dd_train_idx, d.n_drug, d.dd_train_range, check_status=check_status,
                                         packed_out=self._neg_packed)
-            self.embeddings = self._encode()
+            if not ENCODER_FIRST:
+                self.embeddings = self._encode()
             return ops.pair_bce_loss(self.embeddings, self.decoder.weight, plan, self._neg_packed, neg_stream=side)
         # ---- general path: typed CSR of the fresh negatives + segment decoder (large graphs, unmirrored edge sets)
         self._neg_packed = None

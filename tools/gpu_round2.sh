@@ -27,7 +27,7 @@ TIPB_DUMP_WORKLOAD=$O/${TAG}_workload.json timeout 600 ncu --metrics $M --clock-
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_pair_pass|k_rgcn_node|k_seg_aggregate_flat|k_window_scan|k_materialize_main' \
     -s $SKIP_TOP -c 11 -f -o /tmp/${TAG}_top python tools/one_step.py 3 > $O/${TAG}_top.log 2>&1; echo "full capture rc=$?"
 ncu -i /tmp/${TAG}_top.ncu-rep --page raw --csv > $O/${TAG}_top_raw.csv 2>/dev/null
-for k in k_pair_pass k_rgcn_node_fwd_tiled k_rgcn_node_bwd_tiled; do
+for k in k_pair_pass k_rgcn_node_fwd_tc k_rgcn_node_bwd_tc k_seg_aggregate_flat; do
     ncu -i /tmp/${TAG}_top.ncu-rep --page source --csv --kernel-name regex:$k --launch-count 1 > $O/${TAG}_src_$k.csv 2>/dev/null
 done
 timeout 200 python tools/ubench_sweep.py > $O/${TAG}_sweep.json 2> $O/${TAG}_sweep.err; cat $O/${TAG}_sweep.json
