@@ -515,49 +515,66 @@ k_chain_stitch(const int64_t* __restrict__ table, const int* __restrict__ F, con
     if (b == nb - 1) chain_out[0] = o;
 }
 
-// rounds 0 and 1, one thread per draw
+// rounds 0 and 1, one thread per draw.  A CTA takes MAT_TRIPS x 256 consecutive draws: the relation of its first draw
+// is found once (the first version searched per 256 draws, ten dependent loads in front of every CTA -- 27 waves of
+// CTAs that lived for that search: 94 us for 133 MB of traffic) by a 32-way search, and every thread walks forward
+// from it (its draws increase).
+constexpr int MAT_TRIPS = 16;
+
 __global__ void __launch_bounds__(256)
 k_materialize_main(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                    const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                    const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
                    int r_lo, int64_t e_lo, int64_t e_hi, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
     // draws [e_lo, e_hi) of the relations [r_lo, ...) (a rank's shard; the outputs are indexed from e_lo and hold
-    // n_edges = e_hi - e_lo pairs).  The block's 256 consecutive draws span very few relations: one thread finds the
-    // relation of the first draw (binary search), every thread then walks forward from it
+    // n_edges = e_hi - e_lo pairs)
     __shared__ int s_first;
-    const int64_t e0 = e_lo + int64_t(blockIdx.x) * blockDim.x;
-    if (threadIdx.x == 0) {
+    const int64_t e0 = e_lo + int64_t(blockIdx.x) * (MAT_TRIPS * 256);
+    if (threadIdx.x < 32) {
+        // last relation whose range starts at or before e0: 32-way narrowing of [lo_r, hi_r] (two rounds for 861)
         int lo_r = 0, hi_r = n_rel - 1;
         while (lo_r < hi_r) {
-            int mid = (lo_r + hi_r + 1) >> 1;
-            if (range_list[2 * mid] <= e0) lo_r = mid; else hi_r = mid - 1;
+            const int step = (hi_r - lo_r + 31) / 32;
+            const int cand = min(lo_r + (int(threadIdx.x) + 1) * step, hi_r);
+            const unsigned m = __ballot_sync(FULL, range_list[2 * cand] <= e0);      // monotone over the lanes
+            if (m == 0u) {
+                hi_r = min(lo_r + step - 1, hi_r);
+            } else {
+                const int top = 31 - __clz(m);
+                lo_r = min(lo_r + (top + 1) * step, hi_r);
+                hi_r = min(lo_r + step - 1, hi_r);
+            }
         }
-        s_first = lo_r;
+        if (threadIdx.x == 0) s_first = lo_r;
     }
     __syncthreads();
-    const int64_t e = e0 + threadIdx.x;
-    if (e >= e_hi) return;
     int r = s_first;
-    while (r + 1 < n_rel && range_list[2 * (r + 1)] <= e) ++r;
-    const int64_t start = range_list[2 * r];
-    if (e >= range_list[2 * r + 1]) return;
-    const int o = off[r];
-    if (o < 0) return;
-    const int64_t* tb = table + int64_t(r) * TAB;
-    const int lo = int(tb[0]), k = int(tb[5]);
-    const int* nhi = NHI + tb[3];
-    const int i = int(e - start);
-    int p = A[o + i];
-    // membership of a window entry is what k_window_scan already decided: entry x is a positive pair iff the
-    // non-member count does not move at x.  Two coalesced loads instead of a random bitmap probe per draw.
-    const int x0 = o - lo, x = x0 + i;
-    const int cur = nhi[x], prev = x == 0 ? 0 : nhi[x - 1];
-    if (cur == prev) {
-        const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
-        const int hits_incl = (i + 1) - (cur - rb);
-        p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
+    const float fn = float(n_nodes);
+#pragma unroll 1
+    for (int it = 0; it < MAT_TRIPS; ++it) {
+        const int64_t e = e0 + it * 256 + threadIdx.x;
+        if (e >= e_hi) return;
+        while (r + 1 < n_rel && range_list[2 * (r + 1)] <= e) ++r;
+        const int64_t start = range_list[2 * r];
+        if (e >= range_list[2 * r + 1]) continue;
+        const int o = off[r];
+        if (o < 0) continue;
+        const int64_t* tb = table + int64_t(r) * TAB;
+        const int lo = int(tb[0]), k = int(tb[5]);
+        const int* nhi = NHI + tb[3];
+        const int i = int(e - start);
+        int p = A[o + i];
+        // membership of a window entry is what k_window_scan already decided: entry x is a positive pair iff the
+        // non-member count does not move at x.  Two coalesced loads instead of a random bitmap probe per draw.
+        const int x0 = o - lo, x = x0 + i;
+        const int cur = nhi[x], prev = x == 0 ? 0 : nhi[x - 1];
+        if (cur == prev) {
+            const int rb = x0 == 0 ? 0 : nhi[x0 - 1];
+            const int hits_incl = (i + 1) - (cur - rb);
+            p = A[o + k + hits_incl - 1];  // the (hits_incl)-th value of round 1
+        }
+        write_pair(out, packed, n_edges, e - e_lo, p, n_nodes, fn);
     }
-    write_pair(out, packed, n_edges, e - e_lo, p, n_nodes, float(n_nodes));
 }
 
 // rounds >= 2, one CTA per relation
@@ -565,8 +582,9 @@ __global__ void __launch_bounds__(256)
 k_materialize_fixup(const int* __restrict__ A, const uint32_t* __restrict__ member, int64_t words_per_rel,
                     const int64_t* __restrict__ range_list, const int64_t* __restrict__ table,
                     const int* __restrict__ off, const int* __restrict__ NHI, int n_rel, int n_nodes, int64_t n_edges,
-                    int r_lo, int64_t e_lo, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
-    const int r = r_lo + blockIdx.x;
+                    int r_lo, int64_t e_lo, int by_order, int64_t* __restrict__ out, uint32_t* __restrict__ packed) {
+    // unsharded launches take the relations longest window first (table column 7), as k_window_scan does
+    const int r = by_order ? int(table[int64_t(blockIdx.x) * TAB + 7]) : r_lo + blockIdx.x;
     if (r >= n_rel) return;
     const int o = off[r];
     const int64_t* tb = table + int64_t(r) * TAB;
@@ -1092,11 +1110,11 @@ int tipb_neg_sample(uint32_t* mt_state, const uint32_t* stream_words, int64_t n_
             k_chain_walk<<<1, 32, smem, s>>>(table, w.F, (int)n_rel, w.off, w.chain_out, call_status);
         }
         if (n_edges > 0)
-            k_materialize_main<<<(unsigned)ceil_div(n_edges, T), T, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
+            k_materialize_main<<<(unsigned)ceil_div(n_edges, MAT_TRIPS * 256), 256, 0, s>>>(w.A, member, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, n_edges, 0,
                                                                            0, n_edges, neg_edge_index, neg_packed);
         k_materialize_fixup<<<(unsigned)n_rel, T, 0, s>>>(w.A, member, wpr, range_list, table, w.off, w.NHI, (int)n_rel,
-                                                          (int)n_nodes, n_edges, 0, 0, neg_edge_index, neg_packed);
+                                                          (int)n_nodes, n_edges, 0, 0, 1, neg_edge_index, neg_packed);
     }
     k_finalize<<<1, ACC_THREADS, 0, s>>>(stream_words, n_words, mask, max_val, w.flags, (int)n_chunks, w.chain_out, call_status,
                                          status, mt_state);
@@ -1183,12 +1201,12 @@ int tipb_neg_sample_shard_end(uint32_t* mt_state, const uint32_t* stream_words, 
                                                    w.chain_out, w.call_status);
     const int64_t e_local = e_hi - e_lo;      // = the edges of the relations [r_lo, r_hi) = first_rel[rank .. rank + 1]
     if (e_local > 0)
-        k_materialize_main<<<(unsigned)ceil_div(e_local, 256), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off,
+        k_materialize_main<<<(unsigned)ceil_div(e_local, MAT_TRIPS * 256), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off,
                                                                            w.NHI, (int)n_rel, (int)n_nodes, e_local,
                                                                            (int)r_lo, e_lo, e_hi, neg_local, packed_local);
     if (r_hi > r_lo)
         k_materialize_fixup<<<(unsigned)(r_hi - r_lo), 256, 0, s>>>(w.A, member_local, wpr, range_list, table, w.off, w.NHI,
-                                                                  (int)r_hi, (int)n_nodes, e_local, (int)r_lo, e_lo,
+                                                                  (int)r_hi, (int)n_nodes, e_local, (int)r_lo, e_lo, 0,
                                                                   neg_local, packed_local);
     k_finalize<<<1, ACC_THREADS, 0, s>>>(stream_words, n_words, mask, max_val, w.flags, (int)ceil_div(n_words, ACC_CHUNK), w.chain_out,
                                          w.call_status, status, mt_state);
