@@ -36,6 +36,8 @@ SERIAL_STREAMS = False    # measurement aid (bench.py): keep every kernel of a s
 # gaps: 1.98 -> 1.86 ms per step (profiles/r03m_*).  TIPB_SIDE_PRIORITY overrides it for measurements.
 SIDE_PRIORITY = int(os.environ.get("TIPB_SIDE_PRIORITY", "0"))
 ENCODER_FIRST = os.environ.get("TIPB_ENCODER_FIRST", "1") != "0"
+# FMEncoder: run the second P-P GCN layer only into the rows the hierarchy conv reads (exact; TIPB_PP_READ_ROWS=0: all rows)
+PP_READ_ROWS_ONLY = os.environ.get("TIPB_PP_READ_ROWS", "1") != "0"
 
 
 def _require_cuda(t, who):
@@ -199,11 +201,17 @@ class GCNConv(nn.Module):
             return ops.sparse_matmul(x, ops.transpose2d(self.lin.weight))   # general sparse features
         return ops.matmul(x, self.lin.weight, trans_b=True)
 
-    def forward(self, x, edge_index, _fused_relu=False, _pad_rows=0):
+    def forward(self, x, edge_index, _fused_relu=False, _pad_rows=0, _row_plans=None):
         assert edge_index.dtype == torch.long and edge_index.dim() == 2 and edge_index.size(0) == 2
         if not edge_index.is_cuda:
             raise TipbError("GCNConv: CUDA tensors only -- tip_b200 has no CPU fallback")
         plan_dst, plan_src, dis = self._graph(edge_index, x.size(0))
+        if _row_plans is not None:
+            # the caller reads only some rows of the result (FMEncoder: the proteins with a P->D edge): the plans of the
+            # edges INTO those rows, with the normalisation of the whole graph.  The other rows come out as their self
+            # term + bias and take no gradient; the rows that are read are bit for bit the same, the gradients equal up to
+            # the order of their sums (the skipped addends are exact zeros).
+            plan_dst, plan_src = _row_plans
         return ops.gcn_spmm(self._linear(x), self.bias, plan_dst, plan_src, dis, relu=_fused_relu, pad_rows=_pad_rows)
 
 
@@ -217,9 +225,9 @@ class PPEncoder(nn.Module):
         self.conv1 = GCNConv(in_dim, hid1, cached=True)
         self.conv2 = GCNConv(hid1, hid2, cached=True)
 
-    def forward(self, x, edge_index, _pad_rows=0):
+    def forward(self, x, edge_index, _pad_rows=0, _row_plans=None):
         x = self.conv1(x, edge_index, _fused_relu=True)      # bias + ReLU fused into the SpMM epilogue
-        return self.conv2(x, edge_index, _pad_rows=_pad_rows)   # (+ zero rows below: the caller's cat with `hdrug`)
+        return self.conv2(x, edge_index, _pad_rows=_pad_rows, _row_plans=_row_plans)   # (+ zero rows below: the caller's cat with `hdrug`)
 
 
 class FMEncoder(nn.Module):
@@ -243,10 +251,16 @@ class FMEncoder(nn.Module):
         self.rgcn1 = MyRGCNConv2(rgcn_in_dim, n_hid1, num_dd_et, num_base, after_relu=False)
         self.rgcn2 = MyRGCNConv2(n_hid1, n_hid2, num_dd_et, num_base, after_relu=True)
         self._identity_ok = {}
+        self._row_plan_cache = None
         self.reset_parameters()
 
     def reset_parameters(self):
         self.embed.data.normal_()
+
+    def __getstate__(self):      # torch.save(model): device-side caches do not travel
+        state = dict(self.__dict__)
+        state["_row_plan_cache"], state["_identity_ok"] = None, {}
+        return state
 
     def _embed(self, x_drug):
         if x_drug.is_sparse:
@@ -258,13 +272,34 @@ class FMEncoder(nn.Module):
             return ops.sparse_matmul(x_drug, self.embed)            # general sparse drug features (data/utils.py:117-132)
         return ops.matmul(x_drug, self.embed)
 
+    def _read_row_plans(self, pp_edge_index, dp_edge_index, n_prot):
+        """typed CSRs (by target, by source) of the P-P edges whose TARGET protein is the source of a P->D edge: the
+        hierarchy conv reads the second GCN layer's output at those proteins only (19 % of them on the polypharmacy
+        shape), so that layer's SpMM and its backward gather skip everything else.  Built once per graph (re-keyed on
+        the tensors' versions like every other plan); the filtering itself is set-up work on torch index ops."""
+        if not PP_READ_ROWS_ONLY or not pp_edge_index.is_cuda:
+            return None
+        key = (pp_edge_index.data_ptr(), pp_edge_index._version, tuple(pp_edge_index.shape),
+               dp_edge_index.data_ptr(), dp_edge_index._version, tuple(dp_edge_index.shape), int(n_prot))
+        hit = self._row_plan_cache
+        if hit is None or hit[0] != key:
+            src = dp_edge_index[0]
+            read = torch.zeros(n_prot, dtype=torch.bool, device=pp_edge_index.device)
+            read[src[src < n_prot]] = True
+            sub = pp_edge_index[:, read[pp_edge_index[1]]].contiguous()
+            plans = (ops.cached_plan(sub, n_prot, 1, by_src=False, drop_self_loops=True),
+                     ops.cached_plan(sub, n_prot, 1, by_src=True, drop_self_loops=True))
+            hit = self._row_plan_cache = (key, sub, plans, (pp_edge_index, dp_edge_index))
+        return hit[2]
+
     def drug_input(self, x_drug, d_norm, x_prot, pp_edge_index, dp_edge_index, dp_range_list):
         """src/layers.py:529-547: everything in front of the two R-GCN layers"""
+        rows = self._read_row_plans(pp_edge_index, dp_edge_index, x_prot.size(0))
         if self.hdrug._version == self._hdrug_version and self.hdrug.device == pp_edge_index.device:
             # torch.cat((x_prot, hdrug)) with hdrug == 0: the second GCN layer writes into a buffer with zero rows below
-            x_prot = self.pp_encoder(x_prot, pp_edge_index, _pad_rows=self.uni_num_drug)
+            x_prot = self.pp_encoder(x_prot, pp_edge_index, _pad_rows=self.uni_num_drug, _row_plans=rows)
         else:
-            x_prot = self.pp_encoder(x_prot, pp_edge_index)
+            x_prot = self.pp_encoder(x_prot, pp_edge_index, _row_plans=rows)
             x_prot = torch.cat((x_prot, self.hdrug.to(x_prot.device)))
         x_prot = self.hgcn(x_prot, dp_edge_index, dp_range_list)
         return ops.drug_input(self._embed(x_drug), d_norm, x_prot, self.mod)   # / d_norm, then cat | add
