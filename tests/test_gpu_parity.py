@@ -1069,3 +1069,45 @@ def test_pair_pass_applicability():
     broken[0, 3] = (broken[0, 3] + 1) % 50
     assert ops.pair_plan(T(broken, d), 50, 2, T(rl, d), 16) is None      # not mirrored: general path
     assert ops.pair_plan(T(ei, d), 50, 2, T(rl, d), 16) is not None
+
+
+@pytest.mark.gpu
+def test_second_gcn_layer_restricted_to_the_rows_the_hierarchy_reads():
+    """FMEncoder runs PPEncoder.conv2 only into the proteins with a P->D edge (the rows MyHierarchyConv reads,
+    src/layers.py:533-536).  Same embeddings (bit for bit: the rows that are read keep their entry lists) and the same
+    gradients as the unrestricted layer; a graph that is rewritten in place every step is not re-filtered."""
+    from tip_b200 import layers, neg_sampling as ns, synth
+    d = dev()
+    data = synth.make_tip_data(n_drug=80, n_prot=600, n_rel=9, dd_undirected=3000, pp_undirected=4000, pd_edges=150, seed=3)
+    settings = layers.Setting(sp_rate=0.9, lr=0.01, prot_drug_dim=16, n_embed=48, n_hid1=32, n_hid2=16, num_base=32)
+    results = {}
+    for flag in (True, False):
+        layers.PP_READ_ROWS_ONLY = flag
+        try:
+            torch.manual_seed(5)
+            ns.seed(77, d)
+            model = layers.TIP(settings, d, mod="cat", data=data)
+            loss = model()
+            loss.backward()
+            used = model.encoder._row_plan_cache is not None and model.encoder._row_plan_cache[2] is not None
+            assert used == flag
+            results[flag] = (model.embeddings.detach().clone(), float(loss),
+                             {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+            if flag:
+                plans = model.encoder._row_plan_cache[2]
+                full = model.encoder.pp_encoder.conv2._cache[0]
+                assert 0 < plans[0].n_entries < full.n_entries
+                # rewritten in place before every step: no re-filtering, the full plans are used
+                model.data.pp_train_indices.copy_(model.data.pp_train_indices.clone())
+                assert model.encoder._read_row_plans(model.data.pp_train_indices, model.data.dp_edge_index, data["n_prot"]) is None
+                model.data.pp_train_indices.copy_(model.data.pp_train_indices.clone())
+                assert model.encoder._read_row_plans(model.data.pp_train_indices, model.data.dp_edge_index, data["n_prot"]) is None
+                # left alone for a step: filtered again
+                assert model.encoder._read_row_plans(model.data.pp_train_indices, model.data.dp_edge_index, data["n_prot"]) is not None
+        finally:
+            layers.PP_READ_ROWS_ONLY = True
+    z1, l1, g1 = results[True]
+    z0, l0, g0 = results[False]
+    assert torch.equal(z1, z0) and l1 == l0
+    for n in g0:
+        close(g1[n], g0[n].cpu().numpy(), rtol=1e-5, what="grad " + n)
