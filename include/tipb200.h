@@ -212,7 +212,7 @@ int tipb_neg_bitmap_build(const int64_t* pos_edge_index, const int64_t* range_li
                           int64_t n_nodes, int64_t n_rel, uint32_t* member, int32_t* popcount /* [n_rel] */,
                           void* stream);
 int tipb_neg_table_build(const int64_t* range_list_host, const int32_t* popcount_host, int64_t n_rel,
-                         int64_t n_nodes, double z_sigma, int64_t* table_host /* [n_rel*7] */,
+                         int64_t n_nodes, double z_sigma, int64_t* table_host /* [n_rel*8] */,
                          int64_t* totals_host /* [4] */);
 size_t tipb_neg_sample_workspace_bytes(int64_t n_edges, int64_t n_rel, int64_t n_words, int64_t sum_l,
                                        int64_t sum_w);
