@@ -232,3 +232,45 @@ def test_fullscale_oracle_form_equals_the_structural_form():
         torch.testing.assert_close(z1, z0, rtol=1e-10, atol=1e-13)
         for k in g0:
             torch.testing.assert_close(g1[k], g0[k], rtol=1e-9, atol=1e-12 * float(g0[k].abs().max()), msg=lambda m: k + ": " + m)
+
+
+def test_only_proteins_with_a_drug_edge_need_the_second_gcn_layer():
+    """tip_b200.layers.FMEncoder runs PPEncoder.conv2 only over the P-P edges INTO proteins that are the source of a
+    P->D edge, with the normalisation of the whole graph.  In the reference's formulation (oracle restatement of
+    src/layers.py:391-395 and :229-242, float64): the hierarchy conv's output and the gradients of every parameter are
+    the same whether conv2 aggregates over all edges or over that subset -- the other rows are never read."""
+    from oracle import tip_oracle as to
+    rng = np.random.default_rng(4)
+    n_prot, n_drug = 300, 40
+    pp = rng.integers(0, n_prot, size=(2, 1500))
+    pp = np.concatenate([pp, pp[::-1]], axis=1)
+    src = rng.choice(n_prot, size=60, replace=False)[rng.integers(0, 60, size=150)]
+    dp = np.stack([src, n_prot + rng.integers(0, n_drug, size=150)])
+    pp_t, dp_t = torch.from_numpy(pp), torch.from_numpy(dp)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(n_prot, 24, generator=gen, dtype=torch.float64)
+
+    def run(restrict):
+        w1 = (torch.randn(32, 24, generator=torch.Generator().manual_seed(1), dtype=torch.float64) * 0.2).requires_grad_(True)
+        b1 = (torch.randn(32, generator=torch.Generator().manual_seed(2), dtype=torch.float64) * 0.1).requires_grad_(True)
+        w2 = (torch.randn(16, 32, generator=torch.Generator().manual_seed(3), dtype=torch.float64) * 0.2).requires_grad_(True)
+        b2 = (torch.randn(16, generator=torch.Generator().manual_seed(4), dtype=torch.float64) * 0.1).requires_grad_(True)
+        wh = (torch.randn(16, 8, generator=torch.Generator().manual_seed(5), dtype=torch.float64) * 0.3).requires_grad_(True)
+        row, col, w = to.gcn_norm(pp_t, n_prot, torch.float64)
+        h = torch.relu(to.gcn_conv(x, (row, col, w), w1, b1))
+        if restrict:
+            read = torch.zeros(n_prot, dtype=torch.bool)
+            read[dp_t[0]] = True
+            keep = read[col]                      # edges (incl. the self loops gcn_norm added) INTO a protein that is read
+            assert 0 < int(keep.sum()) < keep.numel()
+            row, col, w = row[keep], col[keep], w[keep]
+        x2 = to.gcn_conv(h, (row, col, w), w2, b2)
+        out = to.hier_conv(torch.cat([x2, torch.zeros(n_drug, 16, dtype=torch.float64)]), dp_t, wh, n_prot, n_drug)
+        (out * torch.arange(1, out.numel() + 1, dtype=torch.float64).reshape(out.shape)).sum().backward()
+        return out.detach(), [p.grad for p in (w1, b1, w2, b2, wh)]
+
+    out_full, g_full = run(False)
+    out_sub, g_sub = run(True)
+    torch.testing.assert_close(out_sub, out_full, rtol=0, atol=0)
+    for a, b in zip(g_sub, g_full):
+        torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-14)
