@@ -24,6 +24,7 @@ FAMILIES = [
 def short_name(name):
     name = re.sub(r"\(.*", "", name)
     name = name.replace("void ", "").replace("tipb::", "")
+    name = name.replace("(bool)1", "true").replace("(bool)0", "false")      # ncu prints template bools as (bool)1
     return re.sub(r"\(int\)|\(bool\)", "", name).strip()
 
 
