@@ -34,6 +34,11 @@ for r in rows[2:]:
 kernels = {k: {"launches_in_capture": a["launches"], "dram_read_bytes": int(a["rd"] / a["launches"]),
                "dram_write_bytes": int(a["wr"] / a["launches"]), "traffic_bytes": int((a["rd"] + a["wr"]) / a["launches"]),
                "ncu_duration_us": round(a["us"] / a["launches"], 2)} for k, a in agg.items()}
+# ncu prints a bool template argument as 1 / 0, CUPTI (bench.py) as true / false: alias those names
+for k in list(kernels):
+    for a, b in (("<1>", "<true>"), ("<0>", "<false>")):
+        if k.endswith(a) and k[:-len(a)] + b not in kernels:
+            kernels[k[:-len(a)] + b] = kernels[k]
 json.dump({"source": note or raw, "what": "per launch averages; traffic = dram__bytes_read.sum + dram__bytes_write.sum",
            "kernels": kernels}, open(out, "w"), indent=1)
 print("wrote", out, len(kernels), "kernels")
