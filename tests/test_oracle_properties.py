@@ -274,3 +274,38 @@ def test_only_proteins_with_a_drug_edge_need_the_second_gcn_layer():
     torch.testing.assert_close(out_sub, out_full, rtol=0, atol=0)
     for a, b in zip(g_sub, g_full):
         torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-14)
+
+
+def test_gcn_and_hierarchy_oracle_against_dense_textbook_forms():
+    """Independent witness for the third-party half of rows A4 / A5 (PyG's GCNConv is not installable here): the
+    oracle's gcn_norm / gcn_conv equal the textbook GCN  D^-1/2 (A + I) D^-1/2 X W^T + b  built densely with scipy
+    (multi-edges counted with their multiplicity, existing self loops replaced by one, as add_remaining_self_loops
+    does with unit weights), and hier_conv equals a dense row-normalised adjacency product."""
+    import scipy.sparse as sp
+    from oracle import tip_oracle as to
+    rng = np.random.default_rng(11)
+    n, e, fi, fo = 70, 500, 12, 7
+    ei = rng.integers(0, n, size=(2, e))
+    ei[:, :5] = np.stack([np.arange(5), np.arange(5)])          # a few self loops
+    ei = np.concatenate([ei, ei[:, :40]], axis=1)                # and duplicated edges
+    x = rng.standard_normal((n, fi))
+    w = rng.standard_normal((fo, fi))
+    b = rng.standard_normal(fo)
+    got = to.gcn_conv(torch.from_numpy(x), to.gcn_norm(torch.from_numpy(ei), n, torch.float64), torch.from_numpy(w),
+                      torch.from_numpy(b)).numpy()
+    keep = ei[0] != ei[1]
+    a = sp.coo_matrix((np.ones(int(keep.sum())), (ei[1][keep], ei[0][keep])), shape=(n, n)).tocsr() + sp.identity(n)
+    dis = 1.0 / np.sqrt(np.asarray(a.sum(axis=1)).ravel())
+    want = (sp.diags(dis) @ a @ sp.diags(dis)) @ (x @ w.T) + b
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+    n_src, n_tgt, fh = 50, 9, 5
+    dp = np.stack([rng.integers(0, n_src, size=120), n_src + rng.integers(0, n_tgt - 1, size=120)])   # last target: no edge
+    xs = rng.standard_normal((n_src + n_tgt, fi))
+    wh = rng.standard_normal((fi, fh))
+    got = to.hier_conv(torch.from_numpy(xs), torch.from_numpy(dp), torch.from_numpy(wh), n_src, n_tgt).numpy()
+    adj = sp.coo_matrix((np.ones(120), (dp[1], dp[0])), shape=(n_src + n_tgt, n_src + n_tgt)).toarray()
+    deg = np.maximum(adj.sum(axis=1, keepdims=True), 1.0)
+    want = ((adj / deg) @ xs)[n_src:] @ wh
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    assert np.all(got[-1] == 0.0)
