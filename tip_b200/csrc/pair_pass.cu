@@ -31,7 +31,6 @@ constexpr int PP_WARPS = PP_THREADS / 32;
 constexpr int PP_T = 2048;               // pairs per tile
 constexpr int PP_E = 2 * PP_T;           // pair-ends per tile: [0, T) row side, [T, 2T) column side
 constexpr int PP_ROUNDS = PP_E / PP_THREADS;   // pair-ends (and ranking rounds) per thread / warp: 8
-constexpr uint16_t PP_INVALID = 0xffffu;
 
 // row `row`, float4 column q of a [n][Q] float4 matrix staged with an XOR swizzle on q: rows are 16*Q bytes apart, so
 // without it the 8 lanes of a quarter-warp gathering random rows at one q would share 2 (Q = 4) bank groups

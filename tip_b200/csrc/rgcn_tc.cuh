@@ -76,7 +76,7 @@ k_rgcn_node_fwd_tc(const int* __restrict__ node_ptr, const int* __restrict__ seg
         if (!(dbg & 128))
         for (int k = tid; k < LY::NS * LY::STAGE / 16; k += RT_THREADS) reinterpret_cast<uint4*>(stage0)[k] = make_uint4(0u, 0u, 0u, 0u);
     } else if (F < RT_M) {
-        constexpr int Z16 = (RT_M - F) / 8 * RT_SBO / 16;           // 16-byte words per piece
+        constexpr int Z16 = F < RT_M ? (RT_M - F) / 8 * RT_SBO / 16 : 1;   // 16-byte words per piece (branch is dead for F = 64)
         for (int k = tid; k < 3 * LY::NS * Z16; k += RT_THREADS) {
             const int piece = k / Z16, w = k % Z16;               // piece = stage * 3 + piece index
             uint8_t* base = stage0 + (piece / 3) * LY::STAGE + (piece % 3) * LY::A_PIECE + (F / 8) * RT_SBO;
